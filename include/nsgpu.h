@@ -1,0 +1,166 @@
+/*
+ * nsgpu.h -- C ABI of libnsgpu.so: B200-native (sm_100a) residual / Jacobian assembly of the
+ * stabilized incompressible Navier-Stokes weak forms, CSR sparsity construction, CSR SpMV and
+ * ghost (halo) exchange.  Plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *
+ * Each entry point names the reference interface it replaces (file:line into the reference
+ * repository mungerct/Stabilized_Navier_Stokes_Flow_FEniCSx).  "dolfinx" below means the un-vendored
+ * fenics-dolfinx 0.9.0 the reference scripts call.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative NSGPU_E* code; the message is available
+ *     from nsgpu_last_error().  Nothing throws or aborts across the ABI.
+ *   - one context per GPU per host thread/process (= one MPI rank = one mesh partition).  Calls on a
+ *     context are serialised on its CUDA stream and are synchronous on return unless noted.
+ *   - the caller owns every host array; set_* calls copy to the device; x / F / vals arguments of the
+ *     compute calls are borrowed for the duration of the call.
+ *   - *_dev variants take device pointers (zero-copy; used by the device-resident Krylov loop and the
+ *     throughput benchmark).
+ *   - array layout is exactly what dolfinx exposes: geometry x (n_nodes x 3, padded), geometry dofmap
+ *     (cells x nodes_per_cell int32), W.dofmap.list (cells x ndofs_cell int32, block size 1), owned
+ *     dofs first then ghosts; owned cells first then ghost cells.
+ */
+#ifndef NSGPU_H
+#define NSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsgpu_ctx nsgpu_ctx;
+
+enum {
+  NSGPU_OK = 0,
+  NSGPU_EINVAL = -1,   /* bad argument / call order */
+  NSGPU_ECUDA = -2,    /* CUDA runtime error (no device, OOM, launch failure) */
+  NSGPU_EUNSUPPORTED = -3,
+  NSGPU_ENCCL = -4,
+  NSGPU_EPATTERN = -5  /* element entry outside the sparsity pattern / row too long */
+};
+
+/* weak-form flavours (nsgpu_set_form) */
+enum {
+  NSGPU_FORM_GMETRIC = 0, /* G-metric SUPG/PSPG/LSIC NS: NavierStokes/NavierStokesChannelFlow.py:220-251 */
+  NSGPU_FORM_UGN = 1,     /* h-based UGN SUPG/PSPG/LSIC NS: LidDrivenFlow/LidDrivenNavierStokesFlow.py:112-143 */
+  NSGPU_FORM_STOKES = 2   /* alpha grad u:grad v + sp(-p div v + q div u) + beta h^2 grad p.grad q:
+                             NavierStokesChannelFlow.py:160-172, LidDrivenNavierStokesFlow.py:86-99,
+                             StokesFlow/DuctStokesFlow.py:188-192 */
+};
+
+/* assembly kernel selection (nsgpu_set_option "kernel") */
+enum {
+  NSGPU_KERNEL_AUTO = 0,
+  NSGPU_KERNEL_GENERIC = 1,  /* one thread per (cell, test dof), direct quadrature, any element/form */
+  NSGPU_KERNEL_FAST = 2      /* factorised P1-P1 tet G-metric kernels */
+};
+
+int nsgpu_version(void);
+
+/* Lifetime.  device = CUDA ordinal. */
+int nsgpu_create(nsgpu_ctx** out, int device);
+int nsgpu_destroy(nsgpu_ctx* ctx);
+/* Last error text of ctx (or of the failed nsgpu_create when ctx == NULL). Never NULL. */
+const char* nsgpu_last_error(const nsgpu_ctx* ctx);
+
+/* mesh.geometry.x / mesh.geometry.dofmap of the rank-local mesh produced by
+ * gmshio.model_to_mesh (NavierStokesChannelFlow.py:111) or create_rectangle
+ * (LidDrivenNavierStokesFlow.py:29-30).  gdim = 2 (triangles) or 3 (tetrahedra); affine cells. */
+int nsgpu_set_mesh(nsgpu_ctx* ctx, int gdim, int64_t n_nodes, const double* x /* n_nodes*3 */,
+                   int64_t n_cells_owned, int64_t n_cells_total, const int32_t* x_dofmap /* n_cells_total*(gdim+1) */);
+
+/* W = functionspace(msh, mixed_element([P_vdeg^gdim, P1])) (NavierStokesChannelFlow.py:128-129):
+ * W.dofmap.list (block size 1; cell-local order = velocity node-major, components interleaved, then
+ * pressure) and the index-map sizes.  vdeg = 1 (stabilized P1-P1) or 2 (Taylor-Hood P2-P1). */
+int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap /* n_cells_total*ndofs_cell */,
+                    int64_t n_dofs_owned, int64_t n_dofs_ghost);
+
+/* The UFL form text of define_navier_stokes_form (NavierStokesChannelFlow.py:220-266) reduced to its
+ * parameters: nu = 1/Re (:223), Ci = 36 (:237).  alpha/sp/beta are used by NSGPU_FORM_STOKES only.
+ * May be called again at any time (Reynolds sweep of run_all_RE.sh) without rebuilding anything. */
+int nsgpu_set_form(nsgpu_ctx* ctx, int flavour, double nu, double Ci, double alpha, double sp, double beta);
+
+/* bcs = [bc_wall, bc_inlet_1, bc_inlet_2, bc_outlet] (NavierStokesChannelFlow.py:134-146): one
+ * (dofs, values) segment per dirichletbc object, in list order; a dof may appear in several objects
+ * (multiplicity is preserved: assemble_matrix adds 1.0 on the diagonal per object). */
+int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr /* n_bc+1 */, const int32_t* bc_dofs, const double* bc_vals);
+
+/* create_matrix(problem.a) (NavierStokesChannelFlow.py:272): CSR sparsity = union over owned cells of
+ * dofs x dofs, rows = owned + ghost dofs, columns sorted by local index.  nnz_out may be NULL. */
+int nsgpu_build_pattern(nsgpu_ctx* ctx, int64_t* nnz_out);
+int nsgpu_get_pattern(nsgpu_ctx* ctx, int64_t* indptr /* n_rows+1 */, int32_t* indices /* nnz */);
+int nsgpu_pattern_sizes(nsgpu_ctx* ctx, int64_t* n_rows, int64_t* nnz);
+
+/* NonlinearPDE_SNESProblem.F (NavierStokesChannelFlow.py:51-67): forward halo of x, zero F,
+ * assemble_vector(F, L), apply_lifting(F, [a], [bc], [x], -1.0), reverse halo-add, set_bc(F, bc, x, -1.0).
+ * x_local: n_owned + n_ghost values (ghost part is overwritten by the forward halo when a communicator
+ * is attached).  F_local: n_owned + n_ghost values out (owned part meaningful). */
+int nsgpu_residual(nsgpu_ctx* ctx, const double* x_local, double* F_local);
+
+/* NonlinearPDE_SNESProblem.J (NavierStokesChannelFlow.py:69-75): J.zeroEntries(),
+ * assemble_matrix(J, a, bcs=bc) incl. BC diagonals, J.assemble() (ghost rows shipped to owners).
+ * vals (nnz, CSR order of nsgpu_get_pattern) may be NULL: the matrix then stays on the device for
+ * nsgpu_spmv (MatShell use). */
+int nsgpu_jacobian(nsgpu_ctx* ctx, const double* x_local, double* vals);
+
+/* One pass producing both (what SNES needs at every Newton iterate).  The Jacobian is always assembled;
+ * vals == NULL keeps it on the device, F_local == NULL skips the residual. */
+int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals, double* F_local);
+
+/* MatMult inside KSPTFQMR (snes.getKSP().setType('tfqmr'), NavierStokesChannelFlow.py:282):
+ * y_owned = J x with the Jacobian of the last nsgpu_jacobian*; x: n_owned (+ghost, refreshed by the halo). */
+int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned);
+
+/* Replace the matrix values (e.g. to use nsgpu_spmv with a matrix assembled elsewhere). */
+int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals);
+int nsgpu_get_values(nsgpu_ctx* ctx, double* vals);
+
+/* Device-pointer variants: same semantics, pointers are device memory of ctx's GPU; asynchronous on
+ * ctx's stream (use nsgpu_sync or the stream). */
+int nsgpu_jacobian_residual_dev(nsgpu_ctx* ctx, double* x_local_dev, int want_jacobian, double* F_local_dev);
+int nsgpu_spmv_dev(nsgpu_ctx* ctx, double* x_local_dev, double* y_owned_dev);
+int nsgpu_values_dev(nsgpu_ctx* ctx, double** vals_dev);
+int nsgpu_sync(nsgpu_ctx* ctx);
+void* nsgpu_stream(nsgpu_ctx* ctx); /* cudaStream_t */
+
+/* Device memory helpers for hosts without a CUDA binding (ctypes). */
+int nsgpu_dev_alloc(nsgpu_ctx* ctx, int64_t bytes, void** out);
+int nsgpu_dev_free(nsgpu_ctx* ctx, void* p);
+int nsgpu_memcpy_h2d(nsgpu_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+int nsgpu_host_alloc_pinned(int64_t bytes, void** out);
+int nsgpu_host_free_pinned(void* p);
+
+/* Options: "kernel" (NSGPU_KERNEL_*), "threads" (block size of the assembly kernels). */
+int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
+
+/* Time on ctx's stream, CUDA events: ms of the last call of each phase.
+ * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build. */
+int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n);
+/* Kernel launches issued by this context since creation (bench.py's "gpu_launches"). */
+int64_t nsgpu_launch_count(nsgpu_ctx* ctx);
+/* Device time (ms) of the main kernel(s) of the last *_dev call; synchronises on that call's end event. */
+int nsgpu_last_kernel_ms(nsgpu_ctx* ctx, double* ms);
+
+/* ---- multi-GPU: x.ghostUpdate(INSERT, FORWARD) / F.ghostUpdate(ADD, REVERSE) / J.assemble()
+ *      (NavierStokesChannelFlow.py:57-60, :66, :75) over NCCL ------------------------------------- */
+int nsgpu_comm_unique_id(void* out, int64_t nbytes /* >= 128 */);
+int nsgpu_comm_init(nsgpu_ctx* ctx, int rank, int nranks, const void* unique_id);
+/* Vector halo plan.  For neighbour k: forward sends x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned dofs
+ * ghosted by neigh_rank[k]) and receives into x[recv_idx[recv_ptr[k]..]] (local ghost dofs owned by it);
+ * the reverse (ADD) exchange uses the same lists with the roles swapped. */
+int nsgpu_set_halo(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_rank, const int64_t* send_ptr, const int32_t* send_idx,
+                   const int64_t* recv_ptr, const int32_t* recv_idx);
+/* Ghost-row plan for J.assemble().  For neighbour k: this rank sends the CSR values of its ghost rows
+ * owned by neigh_rank[k], positions send_pos[send_ptr[k]..], and adds what it receives at recv_pos[...]. */
+int nsgpu_set_row_exchange(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_rank, const int64_t* send_ptr, const int64_t* send_pos,
+                           const int64_t* recv_ptr, const int64_t* recv_pos);
+/* Extra (row, col) entries contributed by other ranks' ghost rows (dolfinx SparsityPattern::finalize);
+ * must be called before nsgpu_build_pattern. */
+int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, const int32_t* cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSGPU_H */

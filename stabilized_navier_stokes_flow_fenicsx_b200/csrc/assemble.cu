@@ -1,0 +1,153 @@
+// assemble.cu -- global residual / Jacobian assembly with dolfinx semantics
+// (assemble_vector + apply_lifting + set_bc and assemble_matrix of
+//  NavierStokes/NavierStokesChannelFlow.py:62-67,73-74).
+//
+// Generic path: one thread per (owned cell, test dof).  The thread evaluates its row of the element
+// Jacobian and its residual entry (element_generic.cuh), applies the Dirichlet row/column zeroing and the
+// lifting term, and adds into the CSR values through the precomputed entity-relative position map.
+#include "common.cuh"
+#include "element_p1tet.cuh"
+
+namespace nsgpu {
+
+template <int GD, int VDEG, bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(128)
+k_assemble_generic(int64_t n_cells, FormParams form, const double* __restrict__ xg, const int32_t* __restrict__ cells,
+                   const int32_t* __restrict__ dofmap, const double* __restrict__ wv, const uint8_t* __restrict__ bc_marker,
+                   const double* __restrict__ bc_value, const int64_t* __restrict__ indptr, const uint16_t* __restrict__ rel,
+                   double* __restrict__ vals, double* __restrict__ F) {
+  using T = ElemTraits<GD, VDEG>;
+  constexpr int ND = T::ND;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_cells * ND) return;
+  const int64_t cell = t / ND;
+  const int row = (int)(t - cell * ND);
+
+  double x[3 * (GD + 1)];
+#pragma unroll
+  for (int a = 0; a <= GD; ++a) {
+    const int64_t v = cells[cell * (GD + 1) + a];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) x[3 * a + i] = xg[3 * v + i];
+  }
+  const int32_t* dm = dofmap + cell * ND;
+  double w[ND];
+  bool cell_bc = false;
+  for (int k = 0; k < ND; ++k) {
+    const int32_t d = dm[k];
+    w[k] = wv[d];
+    if (bc_marker) cell_bc |= bc_marker[d] != 0;
+  }
+  const int32_t gi = dm[row];
+  const bool need_A = WANT_J || (WANT_F && cell_bc);  // lifting needs the un-zeroed row
+
+  double Arow[ND];
+  for (int k = 0; k < ND; ++k) Arow[k] = 0.0;
+  double b = 0.0;
+  if (need_A) element_row<GD, VDEG, true, WANT_F>(form, x, w, row, Arow, &b);
+  else element_row<GD, VDEG, false, WANT_F>(form, x, w, row, Arow, &b);
+
+  if (WANT_F) {
+    if (cell_bc) {
+      // apply_lifting(F, [a], [bc], [x], -1.0):  b_e[i] += Ae[i][j] (g_j - x_j) over constrained trial dofs j
+      for (int j = 0; j < ND; ++j) {
+        const int32_t dj = dm[j];
+        if (bc_marker[dj]) b += Arow[j] * (bc_value[dj] - w[j]);
+      }
+    }
+    atomicAdd(F + gi, b);
+  }
+  if (WANT_J) {
+    const bool row_bc = bc_marker && bc_marker[gi];
+    if (!row_bc) {  // constrained test rows are zeroed: nothing to add
+      const int64_t base = indptr[gi];
+      const uint16_t* r = rel + (cell * T::NENT + entity_of_local_dof<GD, VDEG>(row)) * ND;
+      for (int j = 0; j < ND; ++j) {
+        const bool col_bc = cell_bc && bc_marker[dm[j]];
+        if (!col_bc) atomicAdd(vals + base + r[j], Arow[j]);
+      }
+    }
+  }
+}
+
+// assemble_matrix's diagonal pass: +1.0 per DirichletBC object holding the owned dof
+__global__ void k_bc_diagonal(int64_t n_owned, const int32_t* __restrict__ mult, const int64_t* __restrict__ diag, double* vals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_owned && mult[i] > 0 && diag[i] >= 0) vals[diag[i]] += (double)mult[i];
+}
+
+// set_bc(F, bc, x, -1.0):  F[dof] = -(g - x[dof]) on owned constrained dofs
+__global__ void k_set_bc(int64_t n_owned, const uint8_t* __restrict__ marker, const double* __restrict__ value,
+                         const double* __restrict__ xv, double* F) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_owned && marker[i]) F[i] = xv[i] - value[i];
+}
+
+template <int GD, int VDEG>
+static void launch_generic(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_F) {
+  using T = ElemTraits<GD, VDEG>;
+  const int bs = 128;
+  const int64_t nthreads = ctx->n_cells_owned * T::ND;
+  const unsigned grid = (unsigned)ceil_div(nthreads > 0 ? nthreads : 1, bs);
+  const uint8_t* mk = ctx->has_bc ? ctx->d_bc_marker : nullptr;
+#define NS_LAUNCH(J, F)                                                                                           \
+  k_assemble_generic<GD, VDEG, J, F><<<grid, bs, 0, ctx->stream>>>(ctx->n_cells_owned, ctx->form, ctx->d_x, ctx->d_cells, \
+      ctx->d_dofmap, d_xin, mk, ctx->d_bc_value, ctx->d_indptr, ctx->d_rel, ctx->d_vals, d_F)
+  if (want_J && want_F) NS_LAUNCH(true, true);
+  else if (want_J) NS_LAUNCH(true, false);
+  else NS_LAUNCH(false, true);
+#undef NS_LAUNCH
+  ctx->launches += 1;
+}
+
+// d_xin: n_dofs state (halo already refreshed).  d_Fout: n_dofs residual (zeroed here).
+int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
+  cudaStream_t s = ctx->stream;
+  if (want_J) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));   // J.zeroEntries()
+  if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_dofs, s));                          // f_local.set(0.0)
+  NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+
+  bool fast = false;
+  if (ctx->gdim == 3 && ctx->vdeg == 1 && ctx->form.flavour == NSGPU_FORM_GMETRIC && ctx->kernel_sel != NSGPU_KERNEL_GENERIC)
+    fast = p1tet_fast_available(ctx);
+  if (ctx->kernel_sel == NSGPU_KERNEL_FAST && !fast) {
+    set_error(ctx, "kernel=fast requested but the factorised kernel does not apply to this element/form");
+    return NSGPU_EUNSUPPORTED;
+  }
+  if (fast) {
+    int rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout);
+    if (rc != NSGPU_OK) return rc;
+  } else {
+    const int key = ctx->gdim * 10 + ctx->vdeg;
+    switch (key) {
+      case 31: launch_generic<3, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 32: launch_generic<3, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 21: launch_generic<2, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 22: launch_generic<2, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      default: set_error(ctx, "unsupported element"); return NSGPU_EUNSUPPORTED;
+    }
+  }
+  NS_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+  NS_CUDA(ctx, cudaGetLastError());
+
+  if (want_J) {
+    int rc = rows_exchange_add(ctx);   // J.assemble(): ghost rows -> owners
+    if (rc != NSGPU_OK) return rc;
+    if (ctx->has_bc) {
+      k_bc_diagonal<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, s>>>(ctx->n_owned, ctx->d_bc_mult, ctx->d_diag, ctx->d_vals);
+      ctx->launches += 1;
+    }
+  }
+  if (want_F) {
+    int rc = halo_reverse_add(ctx, d_Fout);   // F.ghostUpdate(ADD, REVERSE)
+    if (rc != NSGPU_OK) return rc;
+    if (ctx->has_bc) {
+      k_set_bc<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, s>>>(ctx->n_owned, ctx->d_bc_marker, ctx->d_bc_value, d_xin, d_Fout);
+      ctx->launches += 1;
+    }
+  }
+  NS_CUDA(ctx, cudaGetLastError());
+  return NSGPU_OK;
+}
+
+}  // namespace nsgpu

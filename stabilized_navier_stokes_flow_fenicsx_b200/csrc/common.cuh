@@ -1,0 +1,134 @@
+// common.cuh -- context object and small helpers shared by the translation units of libnsgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nsgpu.h"
+#include "element_generic.cuh"
+
+namespace nsgpu {
+
+constexpr int KMAX = 4;        // max dofs on one mesh entity (vertex of a 3-D mixed space: 3 velocity + 1 pressure)
+constexpr int MAX_NEIGH = 16;  // neighbouring ranks in the halo plans
+
+struct HaloPlan {
+  int n_neigh = 0;
+  std::vector<int> rank;
+  std::vector<int64_t> send_ptr, recv_ptr;   // host copies (n_neigh+1)
+  int32_t* d_send_idx = nullptr;
+  int32_t* d_recv_idx = nullptr;
+  double* d_send_buf = nullptr;
+  double* d_recv_buf = nullptr;
+};
+
+struct RowPlan {
+  int n_neigh = 0;
+  std::vector<int> rank;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  int64_t* d_send_pos = nullptr;
+  int64_t* d_recv_pos = nullptr;
+  double* d_send_buf = nullptr;
+  double* d_recv_buf = nullptr;
+};
+
+}  // namespace nsgpu
+
+struct nsgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // mesh (nsgpu_set_mesh)
+  int gdim = 0;
+  int64_t n_nodes = 0, n_cells_owned = 0, n_cells_total = 0;
+  double* d_x = nullptr;        // n_nodes x 3
+  int32_t* d_cells = nullptr;   // n_cells_total x (gdim+1)
+
+  // space (nsgpu_set_space)
+  int vdeg = 0, nd = 0, nent = 0;
+  int64_t n_owned = 0, n_ghost = 0, n_dofs = 0;
+  int32_t* d_dofmap = nullptr;  // n_cells_total x nd
+
+  // form
+  nsgpu::FormParams form{0, 0.1, 36.0, 1.0, 1.0, 0.0};
+  bool form_set = false;
+
+  // Dirichlet data per dof
+  bool has_bc = false;
+  uint8_t* d_bc_marker = nullptr;
+  double* d_bc_value = nullptr;
+  int32_t* d_bc_mult = nullptr;
+
+  // CSR pattern + values + scatter maps
+  bool pattern_built = false;
+  int64_t n_rows = 0, nnz = 0;
+  int64_t* d_indptr = nullptr;
+  int32_t* d_indices = nullptr;
+  double* d_vals = nullptr;
+  uint16_t* d_rel = nullptr;    // [cell][entity][local col] rank of the column inside the entity's rows
+  int64_t* d_diag = nullptr;    // position of (i,i) per row, -1 if absent
+  std::vector<int32_t> extra_rows, extra_cols;  // pattern entries received from other ranks
+
+  // work vectors (n_dofs)
+  double* d_xvec = nullptr;
+  double* d_F = nullptr;
+  double* d_y = nullptr;
+
+  // options
+  int kernel_sel = NSGPU_KERNEL_AUTO;
+  int threads = 128;
+
+  // timing / accounting
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t launches = 0;
+
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  void* nccl_comm = nullptr;
+  nsgpu::HaloPlan halo;
+  nsgpu::RowPlan rows;
+};
+
+namespace nsgpu {
+
+const char* set_error(nsgpu_ctx* ctx, const std::string& msg);
+
+#define NS_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      nsgpu::set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+      return NSGPU_ECUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define NS_REQUIRE(ctx, cond, msg)                                                                 \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      nsgpu::set_error(ctx, msg);                                                                  \
+      return NSGPU_EINVAL;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+template <typename T> int dev_alloc(nsgpu_ctx* ctx, T** p, int64_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n <= 0) n = 1;
+  NS_CUDA(ctx, cudaMalloc((void**)p, sizeof(T) * (size_t)n));
+  return NSGPU_OK;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// implemented in pattern.cu / assemble.cu / spmv.cu / halo.cu
+int build_pattern_impl(nsgpu_ctx* ctx);
+int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);
+int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y);
+int halo_forward(nsgpu_ctx* ctx, double* d_v);
+int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);
+int rows_exchange_add(nsgpu_ctx* ctx);
+void halo_free(nsgpu_ctx* ctx);
+
+}  // namespace nsgpu

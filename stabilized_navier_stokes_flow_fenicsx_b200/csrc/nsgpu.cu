@@ -1,0 +1,396 @@
+// nsgpu.cu -- the C ABI of libnsgpu.so (include/nsgpu.h): context lifetime, data upload, and the
+// F / J / MatMult entry points that replace the dolfinx + PETSc calls of NonlinearPDE_SNESProblem
+// (NavierStokes/NavierStokesChannelFlow.py:40-75).  No exception crosses the boundary.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+using namespace nsgpu;
+
+namespace nsgpu {
+static std::mutex g_err_mu;
+static std::string g_create_err = "";
+
+const char* set_error(nsgpu_ctx* ctx, const std::string& msg) {
+  if (ctx) { ctx->err = msg; return ctx->err.c_str(); }
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_create_err = msg;
+  return g_create_err.c_str();
+}
+}  // namespace nsgpu
+
+#define NS_ENTER(ctx)                                                  \
+  if (!(ctx)) return NSGPU_EINVAL;                                     \
+  NS_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+static int elapsed(nsgpu_ctx* ctx, int slot) {
+  NS_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+  float ms = 0.f;
+  NS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  ctx->ms[slot] = ms;
+  return NSGPU_OK;
+}
+
+extern "C" {
+
+int nsgpu_version(void) { return 100; }
+
+int nsgpu_create(nsgpu_ctx** out, int device) {
+  if (!out) return NSGPU_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                           " (libnsgpu has no CPU fallback; the assembly path needs a B200)");
+    return NSGPU_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error(nullptr, "device ordinal out of range"); return NSGPU_EINVAL; }
+  nsgpu_ctx* ctx = new (std::nothrow) nsgpu_ctx();
+  if (!ctx) return NSGPU_EINVAL;
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess) {
+    set_error(nullptr, std::string("context creation: ") + cudaGetErrorString(e));
+    delete ctx;
+    return NSGPU_ECUDA;
+  }
+  *out = ctx;
+  return NSGPU_OK;
+}
+
+int nsgpu_destroy(nsgpu_ctx* ctx) {
+  if (!ctx) return NSGPU_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  halo_free(ctx);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_cells); cudaFree(ctx->d_dofmap);
+  cudaFree(ctx->d_bc_marker); cudaFree(ctx->d_bc_value); cudaFree(ctx->d_bc_mult);
+  cudaFree(ctx->d_indptr); cudaFree(ctx->d_indices); cudaFree(ctx->d_vals); cudaFree(ctx->d_rel); cudaFree(ctx->d_diag);
+  cudaFree(ctx->d_xvec); cudaFree(ctx->d_F); cudaFree(ctx->d_y);
+  if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+  if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NSGPU_OK;
+}
+
+const char* nsgpu_last_error(const nsgpu_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  return g_create_err.c_str();
+}
+
+int nsgpu_set_mesh(nsgpu_ctx* ctx, int gdim, int64_t n_nodes, const double* x, int64_t n_cells_owned, int64_t n_cells_total,
+                   const int32_t* x_dofmap) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, gdim == 2 || gdim == 3, "set_mesh: gdim must be 2 or 3");
+  NS_REQUIRE(ctx, x && x_dofmap && n_nodes > 0 && n_cells_owned >= 0 && n_cells_total >= n_cells_owned, "set_mesh: bad sizes or NULL arrays");
+  ctx->gdim = gdim; ctx->n_nodes = n_nodes; ctx->n_cells_owned = n_cells_owned; ctx->n_cells_total = n_cells_total;
+  ctx->pattern_built = false;
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_x, n_nodes * 3))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_cells, n_cells_total * (gdim + 1)))) return rc;
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_x, x, sizeof(double) * n_nodes * 3, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_cells, x_dofmap, sizeof(int32_t) * n_cells_total * (gdim + 1), cudaMemcpyHostToDevice));
+  return NSGPU_OK;
+}
+
+int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_dofs_owned, int64_t n_dofs_ghost) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->gdim != 0, "set_space: call set_mesh first");
+  NS_REQUIRE(ctx, vdeg == 1 || vdeg == 2, "set_space: velocity degree must be 1 (P1-P1) or 2 (P2-P1)");
+  NS_REQUIRE(ctx, dofmap && n_dofs_owned > 0 && n_dofs_ghost >= 0, "set_space: bad sizes or NULL dofmap");
+  NS_REQUIRE(ctx, n_dofs_owned + n_dofs_ghost < (int64_t)2147483647, "set_space: local dof count exceeds int32 (dolfinx local indices are int32)");
+  const int gd = ctx->gdim;
+  const int nvn = vdeg == 1 ? gd + 1 : (gd == 3 ? 10 : 6);
+  ctx->vdeg = vdeg; ctx->nd = gd * nvn + gd + 1; ctx->nent = nvn;
+  ctx->n_owned = n_dofs_owned; ctx->n_ghost = n_dofs_ghost; ctx->n_dofs = n_dofs_owned + n_dofs_ghost;
+  ctx->pattern_built = false;
+  ctx->has_bc = false;
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_dofmap, ctx->n_cells_total * ctx->nd))) return rc;
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_dofmap, dofmap, sizeof(int32_t) * ctx->n_cells_total * ctx->nd, cudaMemcpyHostToDevice));
+  if ((rc = dev_alloc(ctx, &ctx->d_xvec, ctx->n_dofs))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_F, ctx->n_dofs))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_y, ctx->n_dofs))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_bc_marker, ctx->n_dofs))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_bc_value, ctx->n_dofs))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_bc_mult, ctx->n_dofs))) return rc;
+  NS_CUDA(ctx, cudaMemset(ctx->d_bc_marker, 0, ctx->n_dofs));
+  NS_CUDA(ctx, cudaMemset(ctx->d_bc_value, 0, sizeof(double) * ctx->n_dofs));
+  NS_CUDA(ctx, cudaMemset(ctx->d_bc_mult, 0, sizeof(int32_t) * ctx->n_dofs));
+  return NSGPU_OK;
+}
+
+int nsgpu_set_form(nsgpu_ctx* ctx, int flavour, double nu, double Ci, double alpha, double sp, double beta) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, flavour >= 0 && flavour <= 2, "set_form: unknown flavour");
+  NS_REQUIRE(ctx, flavour == NSGPU_FORM_STOKES || nu > 0.0, "set_form: nu must be positive");
+  ctx->form = FormParams{flavour, nu, Ci, alpha, sp, beta};
+  ctx->form_set = true;
+  return NSGPU_OK;
+}
+
+int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr, const int32_t* bc_dofs, const double* bc_vals) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->n_dofs > 0, "set_bcs: call set_space first");
+  NS_REQUIRE(ctx, n_bc >= 0 && (n_bc == 0 || (bc_ptr && bc_dofs && bc_vals)), "set_bcs: NULL arrays");
+  std::vector<uint8_t> marker(ctx->n_dofs, 0);
+  std::vector<double> value(ctx->n_dofs, 0.0);
+  std::vector<int32_t> mult(ctx->n_dofs, 0);
+  int64_t total = 0;
+  for (int b = 0; b < n_bc; ++b) {
+    NS_REQUIRE(ctx, bc_ptr[b + 1] >= bc_ptr[b], "set_bcs: bc_ptr must be non-decreasing");
+    for (int64_t k = bc_ptr[b]; k < bc_ptr[b + 1]; ++k) {
+      const int32_t d = bc_dofs[k];
+      NS_REQUIRE(ctx, d >= 0 && d < ctx->n_dofs, "set_bcs: dof index out of range");
+      marker[d] = 1;
+      value[d] = bc_vals[k];   // list order: the last DirichletBC object holding the dof wins
+      mult[d] += 1;
+      ++total;
+    }
+  }
+  ctx->has_bc = total > 0;
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_marker, marker.data(), ctx->n_dofs, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_value, value.data(), sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_mult, mult.data(), sizeof(int32_t) * ctx->n_dofs, cudaMemcpyHostToDevice));
+  return NSGPU_OK;
+}
+
+int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, const int32_t* cols) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, n >= 0 && (n == 0 || (rows && cols)), "add_pattern_entries: NULL arrays");
+  for (int64_t k = 0; k < n; ++k) {
+    NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_dofs && cols[k] >= 0 && cols[k] < ctx->n_dofs, "add_pattern_entries: index out of range");
+  }
+  ctx->extra_rows.insert(ctx->extra_rows.end(), rows, rows + n);
+  ctx->extra_cols.insert(ctx->extra_cols.end(), cols, cols + n);
+  ctx->pattern_built = false;
+  return NSGPU_OK;
+}
+
+int nsgpu_build_pattern(nsgpu_ctx* ctx, int64_t* nnz_out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->d_dofmap != nullptr, "build_pattern: call set_mesh and set_space first");
+  cudaEvent_t a, b;
+  NS_CUDA(ctx, cudaEventCreate(&a));
+  NS_CUDA(ctx, cudaEventCreate(&b));
+  cudaEventRecord(a, ctx->stream);
+  int rc = build_pattern_impl(ctx);
+  cudaEventRecord(b, ctx->stream);
+  cudaEventSynchronize(b);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  ctx->ms[6] = ms;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (rc != NSGPU_OK) return rc;
+  if (nnz_out) *nnz_out = ctx->nnz;
+  return NSGPU_OK;
+}
+
+int nsgpu_pattern_sizes(nsgpu_ctx* ctx, int64_t* n_rows, int64_t* nnz) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "pattern_sizes: call build_pattern first");
+  if (n_rows) *n_rows = ctx->n_rows;
+  if (nnz) *nnz = ctx->nnz;
+  return NSGPU_OK;
+}
+
+int nsgpu_get_pattern(nsgpu_ctx* ctx, int64_t* indptr, int32_t* indices) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "get_pattern: call build_pattern first");
+  NS_REQUIRE(ctx, indptr && indices, "get_pattern: NULL output");
+  NS_CUDA(ctx, cudaMemcpy(indptr, ctx->d_indptr, sizeof(int64_t) * (ctx->n_rows + 1), cudaMemcpyDeviceToHost));
+  if (ctx->nnz) NS_CUDA(ctx, cudaMemcpy(indices, ctx->d_indices, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
+  return NSGPU_OK;
+}
+
+static int ready(nsgpu_ctx* ctx) {
+  NS_REQUIRE(ctx, ctx->pattern_built, "call build_pattern before assembling");
+  NS_REQUIRE(ctx, ctx->form_set, "call set_form before assembling");
+  return NSGPU_OK;
+}
+
+int nsgpu_jacobian_residual_dev(nsgpu_ctx* ctx, double* x_local_dev, int want_jacobian, double* F_local_dev) {
+  NS_ENTER(ctx);
+  int rc = ready(ctx);
+  if (rc) return rc;
+  NS_REQUIRE(ctx, x_local_dev && (want_jacobian || F_local_dev), "jacobian_residual_dev: nothing to do / NULL state");
+  if ((rc = halo_forward(ctx, x_local_dev))) return rc;     // x.ghostUpdate(INSERT, FORWARD)
+  return assemble_impl(ctx, x_local_dev, want_jacobian != 0, F_local_dev != nullptr, F_local_dev);
+}
+
+int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals, double* F_local) {
+  NS_ENTER(ctx);
+  int rc = ready(ctx);
+  if (rc) return rc;
+  NS_REQUIRE(ctx, x_local != nullptr, "x_local is NULL");
+  cudaStream_t s = ctx->stream;
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  // the Jacobian is always assembled; vals == NULL keeps it on the device (MatShell use with nsgpu_spmv)
+  const bool want_F = F_local != nullptr;
+  const bool want_J = true;
+  if ((rc = assemble_impl(ctx, ctx->d_xvec, want_J, want_F, ctx->d_F))) return rc;
+  if (want_F) NS_CUDA(ctx, cudaMemcpyAsync(F_local, ctx->d_F, sizeof(double) * ctx->n_dofs, cudaMemcpyDeviceToHost, s));
+  if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return elapsed(ctx, 0);
+}
+
+int nsgpu_residual(nsgpu_ctx* ctx, const double* x_local, double* F_local) {
+  NS_ENTER(ctx);
+  int rc = ready(ctx);
+  if (rc) return rc;
+  NS_REQUIRE(ctx, x_local && F_local, "residual: NULL argument");
+  cudaStream_t s = ctx->stream;
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  if ((rc = assemble_impl(ctx, ctx->d_xvec, false, true, ctx->d_F))) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(F_local, ctx->d_F, sizeof(double) * ctx->n_dofs, cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return elapsed(ctx, 1);
+}
+
+int nsgpu_jacobian(nsgpu_ctx* ctx, const double* x_local, double* vals) {
+  NS_ENTER(ctx);
+  int rc = ready(ctx);
+  if (rc) return rc;
+  NS_REQUIRE(ctx, x_local != nullptr, "x_local is NULL");
+  cudaStream_t s = ctx->stream;
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  if ((rc = assemble_impl(ctx, ctx->d_xvec, true, false, ctx->d_F))) return rc;
+  if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return elapsed(ctx, 0);
+}
+
+int nsgpu_spmv_dev(nsgpu_ctx* ctx, double* x_local_dev, double* y_owned_dev) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "spmv: call build_pattern first");
+  NS_REQUIRE(ctx, x_local_dev && y_owned_dev, "spmv: NULL argument");
+  int rc;
+  if ((rc = halo_forward(ctx, x_local_dev))) return rc;
+  return spmv_impl(ctx, x_local_dev, y_owned_dev);
+}
+
+int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "spmv: call build_pattern first");
+  NS_REQUIRE(ctx, x_local && y_owned, "spmv: NULL argument");
+  cudaStream_t s = ctx->stream;
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  if ((rc = spmv_impl(ctx, ctx->d_xvec, ctx->d_y))) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(y_owned, ctx->d_y, sizeof(double) * ctx->n_owned, cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return elapsed(ctx, 2);
+}
+
+int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built && vals, "set_values: no pattern or NULL values");
+  NS_CUDA(ctx, cudaMemcpy(ctx->d_vals, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
+  return NSGPU_OK;
+}
+
+int nsgpu_get_values(nsgpu_ctx* ctx, double* vals) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built && vals, "get_values: no pattern or NULL output");
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NS_CUDA(ctx, cudaMemcpy(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost));
+  return NSGPU_OK;
+}
+
+int nsgpu_values_dev(nsgpu_ctx* ctx, double** vals_dev) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built && vals_dev, "values_dev: no pattern");
+  *vals_dev = ctx->d_vals;
+  return NSGPU_OK;
+}
+
+int nsgpu_sync(nsgpu_ctx* ctx) {
+  NS_ENTER(ctx);
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NSGPU_OK;
+}
+
+void* nsgpu_stream(nsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int nsgpu_dev_alloc(nsgpu_ctx* ctx, int64_t bytes, void** out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, out && bytes >= 0, "dev_alloc: bad argument");
+  NS_CUDA(ctx, cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 1)));
+  return NSGPU_OK;
+}
+
+int nsgpu_dev_free(nsgpu_ctx* ctx, void* p) {
+  NS_ENTER(ctx);
+  NS_CUDA(ctx, cudaFree(p));
+  return NSGPU_OK;
+}
+
+int nsgpu_memcpy_h2d(nsgpu_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+  NS_ENTER(ctx);
+  NS_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NSGPU_OK;
+}
+
+int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+  NS_ENTER(ctx);
+  NS_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NSGPU_OK;
+}
+
+int nsgpu_host_alloc_pinned(int64_t bytes, void** out) {
+  if (!out) return NSGPU_EINVAL;
+  cudaError_t e = cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1));
+  if (e != cudaSuccess) { set_error(nullptr, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return NSGPU_ECUDA; }
+  return NSGPU_OK;
+}
+
+int nsgpu_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? NSGPU_OK : NSGPU_ECUDA; }
+
+int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, name != nullptr, "set_option: NULL name");
+  if (!strcmp(name, "kernel")) {
+    NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: kernel must be 0 (auto), 1 (generic) or 2 (fast)");
+    ctx->kernel_sel = (int)value;
+  } else if (!strcmp(name, "threads")) {
+    NS_REQUIRE(ctx, value >= 32 && value <= 1024 && value % 32 == 0, "set_option: threads must be a multiple of 32 in [32,1024]");
+    ctx->threads = (int)value;
+  } else {
+    set_error(ctx, std::string("set_option: unknown option ") + name);
+    return NSGPU_EINVAL;
+  }
+  return NSGPU_OK;
+}
+
+int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ms && n >= 0, "timers: bad argument");
+  for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->ms[i];
+  return NSGPU_OK;
+}
+
+/* time of the kernels of the last *_dev call (the host variants record it themselves) */
+int nsgpu_last_kernel_ms(nsgpu_ctx* ctx, double* ms) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ms != nullptr, "NULL output");
+  NS_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+  float t = 0.f;
+  NS_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+  *ms = t;
+  return NSGPU_OK;
+}
+
+int64_t nsgpu_launch_count(nsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
