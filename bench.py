@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- NS Jacobian+residual assembly throughput (Mcells/s) and HBM-roofline fraction on B200.
+
+A "step" is one pass of the hot path over the whole synthetic structured-tet duct: zero J and F,
+fused Jacobian + residual assembly (incl. lifting, BC rows/cols, BC diagonal, set_bc), i.e. what
+NonlinearPDE_SNESProblem.J + .F do at one Newton iterate (NavierStokes/NavierStokesChannelFlow.py:51-75).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload L|M|S] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); the duct is cut into x-slabs (strong scaling: the total
+mesh is fixed).  One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for the byte model.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # n_cross, n_long  
+    "S": (10, 40),       # 24 000 cells  (mesh length 0.1, domain length 4)
+    "M": (50, 200),      # 3.0 M cells
+    "L": (128, 512),     # 50.33 M cells -- the configuration the metric is quoted on
+}
+NU, CI = 0.1, 36.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(nc, nv, ndof, nnz, nodes_per_cell=4, ndofs_cell=16):
+    """Compulsory traffic (SURVEY 8d / BASELINE.md 3): every input read once, every output written once."""
+    jf = 8 * nnz + 4 * nc * (nodes_per_cell + ndofs_cell) + 24 * nv + 16 * ndof
+    f = 4 * nc * (nodes_per_cell + ndofs_cell) + 24 * nv + 16 * ndof
+    spmv = 12 * nnz + 8 * (ndof + 1) + 8 * ndof + 8 * ndof
+    return jf, f, spmv
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_sample_run(steps, warmup, n_cross, build_pattern_on_gpu):
+    """Oracle (CPU restatement of the reference algorithm, OpenMP over all host cores) on a bounded slab of
+    the same duct: same cross-section and box size as the GPU workload, fewer boxes along the axis."""
+    from oracle import oracle
+    from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+    cores = oracle.num_threads()
+    # ~0.012 Mcells/s/core for J+F measured on the build box; aim at ~3 s of CPU work per step
+    target_cells = max(6 * n_cross * n_cross * 2, int(0.012e6 * cores * 3.0))
+    n_long = max(2, int(round(target_cells / (6.0 * n_cross * n_cross))))
+    length = 4.0 * n_long / WORKLOADS["L"][1] if n_cross == WORKLOADS["L"][0] else 4.0 * n_long / max(n_long, 1)
+    m = M.duct_mesh(n_cross, n_long, length=length)
+    sp = M.mixed_space(m, 1)
+    w, bcs = M.duct_state(sp), M.duct_bcs(sp, length=length)
+    marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs], [b[1] for b in bcs])
+    indptr = indices = None
+    if build_pattern_on_gpu:
+        try:
+            from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler
+            asm = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=1)
+            indptr, indices = asm.create_matrix()
+            asm.close()
+        except Exception:
+            indptr = None
+    if indptr is None:
+        indptr, indices = oracle.build_pattern(sp.dofmap, sp.n_dofs)
+    form = oracle.Form(0, 3, 1, NU, CI)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.assemble_jacobian(form, m.x, m.cells, sp.dofmap, w, indptr, indices, marker, mult)
+        F = oracle.assemble_residual(form, m.x, m.cells, sp.dofmap, w, marker, value)
+        oracle.set_bc(F, [b[0] for b in bcs], [b[1] for b in bcs], w)
+        t = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    return {"value": m.n_cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "cores": cores, "kind": "port",
+            "sample": f"{n_cross}x{n_cross}x{n_long} box slab of the duct ({m.n_cells} cells), oracle J+F incl. CSR insertion by row search, "
+                      f"OpenMP {cores} threads, {len(times)} step(s); restated CPU baseline -- not dolfinx (not installable)",
+            "ms_per_step": ms, "cells": m.n_cells}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cross, n_long = WORKLOADS[args.workload]
+    r = cpu_sample_run(args.steps, min(args.warmup, 1), n_cross, build_pattern_on_gpu=True)
+    line = {"impl": "reference", "metric": "NS Jacobian+residual assembly throughput", "value": r["value"], "unit": "Mcells/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"structured-tet duct {args.workload} ({n_cross}x{n_cross}x{n_long} boxes, P1-P1 G-metric, nu={NU}); bounded sample: {r['sample']}"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+    from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler
+    from stabilized_navier_stokes_flow_fenicsx_b200 import distributed as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    comm = D.Comm.from_env() if world > 1 else D.Comm.single()
+    n_cross, n_long = WORKLOADS[args.workload]
+
+    t_setup = time.perf_counter()
+    part = D.duct_partition(n_cross, n_long, rank, world)          # rank-local slab in dolfinx layout
+    asm = NSAssembler(part.x, part.cells, part.dofmap, vdeg=1, n_dofs_owned=part.n_owned, n_dofs_ghost=part.n_ghost,
+                      n_cells_owned=part.n_cells_owned, device=local_rank)
+    asm.set_form(flavour=0, nu=NU, Ci=CI)
+    asm.set_bcs(part.bcs)
+    if args.kernel is not None:
+        asm.set_option("kernel", args.kernel)
+    D.attach(asm, part, comm)                                       # NCCL communicator + halo / ghost-row plans
+    asm.create_matrix(fetch=False)
+    D.finish_pattern_exchange(asm, part, comm)
+    setup_s = time.perf_counter() - t_setup
+
+    nbytes = 8 * asm.n_dofs
+    x_dev, F_dev, y_dev = asm.dev_alloc(nbytes), asm.dev_alloc(nbytes), asm.dev_alloc(nbytes)
+    asm.h2d(x_dev, part.w)
+
+    def step():
+        asm.jacobian_residual_dev(x_dev, True, F_dev)
+
+    launches0 = None
+    for _ in range(args.warmup):
+        step()
+    asm.sync()
+    comm.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = asm.launch_count()
+    kernel_ms = []
+    asm.timer_start()
+    for _ in range(args.steps):
+        step()
+        if args.per_step_sync:
+            kernel_ms.append(asm.last_kernel_ms())
+    total_ms = asm.timer_stop()
+    asm.sync()
+    comm.barrier()
+    launches = asm.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = comm.max(total_ms / args.steps)
+
+    # dominant kernel alone (CUDA events on the library's stream around the assembly kernel), timed live
+    kms = []
+    for _ in range(min(args.steps, 10)):
+        step()
+        kms.append(asm.last_kernel_ms())
+    kernel_ms_avg = comm.max(float(np.mean(kms)))
+
+    # residual only, SpMV
+    f_ms = []
+    for _ in range(3 + min(args.steps, 10)):
+        asm.jacobian_residual_dev(x_dev, False, F_dev)
+        f_ms.append(asm.last_kernel_ms())
+    f_ms = comm.max(float(np.mean(f_ms[3:])))
+    s_ms = []
+    for _ in range(3 + min(args.steps, 10)):
+        asm.spmv_dev(x_dev, y_dev)
+        s_ms.append(asm.last_kernel_ms())
+    s_ms = comm.max(float(np.mean(s_ms[3:])))
+
+    # end to end through the public host API: pinned x -> H2D -> J+F (J stays resident for MatMult) -> D2H F
+    xh = asm.pinned_empty(asm.n_dofs)
+    Fh = asm.pinned_empty(asm.n_dofs)
+    xh[:] = part.w
+    e2e_steps = max(2, min(args.steps, 5))
+    asm.jacobian_residual(xh, F_out=Fh, fetch_vals=False)
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        asm.jacobian_residual(xh, F_out=Fh, fetch_vals=False)
+    e2e_ms = comm.max(1e3 * (time.perf_counter() - t0) / e2e_steps)
+    f_checksum = float(np.abs(Fh[: asm.n_owned]).sum())
+
+    nc_total = 6 * n_cross * n_cross * n_long
+    nv_total = (n_cross + 1) ** 2 * (n_long + 1)
+    ndof_total = 4 * nv_total
+    nnz_total = comm.sum(part.owned_nnz(asm))
+    b_jf, b_f, b_spmv = algorithmic_bytes(nc_total, nv_total, ndof_total, nnz_total)
+    hbm, how = peaks()
+    hbm_total = hbm * world
+
+    if rank == 0:
+        value = nc_total / (ms_per_step * 1e-3) / 1e6
+        achieved = b_jf / (kernel_ms_avg * 1e-3) / 1e9
+        line = {
+            "metric": "NS Jacobian+residual assembly throughput", "value": value, "unit": "Mcells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"structured-tet duct {args.workload}: {n_cross}x{n_cross}x{n_long} boxes x 6 tets = {nc_total} cells, "
+                                   f"{ndof_total} dofs, nnz {nnz_total}; P1-P1 G-metric SUPG/PSPG/LSIC, nu={NU}, Ci={CI}; "
+                                   f"BCs wall/inlet/outlet; x-slab partition over {world} GPU(s)",
+                       "l2": "inputs larger than L2 (no flush needed)" if b_jf / world > 4 * 126e6 else "working set near L2 size: latency-bound case",
+                       "kernel": asm_kernel_name(asm), "setup_s": round(setup_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_total, "unit": "GB/s", "frac": achieved / hbm_total,
+                         "traffic": None, "peak_source": how, "kernel_ms": kernel_ms_avg, "algorithmic_bytes": b_jf,
+                         "note": "J kernel is FP64-pipe bound as well (SURVEY 8d); see DESIGN.md"},
+            "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
+                              "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
+            "spmv": {"ms": s_ms, "GB/s": b_spmv / (s_ms * 1e-3) / 1e9, "frac": b_spmv / (s_ms * 1e-3) / 1e9 / hbm_total,
+                     "GFLOP/s": 2 * nnz_total / (s_ms * 1e-3) / 1e9},
+            "e2e": {"value": nc_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 8 * ndof_total,
+                    "d2h_bytes_per_step": 8 * ndof_total, "ms_per_step": e2e_ms,
+                    "what": "NSAssembler.jacobian_residual(x_host_pinned) -> F_host; J stays device-resident for MatMult (MatShell mode)",
+                    "F_l1_checksum": f_checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_sample_run(1, 0, n_cross, build_pattern_on_gpu=True)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    for p in (x_dev, F_dev, y_dev):
+        asm.dev_free(p)
+    asm.close()
+    comm.close()
+
+
+def asm_kernel_name(asm):
+    return "auto"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NSGPU_WORKLOAD", "L"), choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", type=int, default=None, help="0 auto, 1 generic, 2 fast")
+    ap.add_argument("--per-step-sync", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,8 @@ int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr /* n_bc+1 */, 
 int nsgpu_build_pattern(nsgpu_ctx* ctx, int64_t* nnz_out);
 int nsgpu_get_pattern(nsgpu_ctx* ctx, int64_t* indptr /* n_rows+1 */, int32_t* indices /* nnz */);
 int nsgpu_pattern_sizes(nsgpu_ctx* ctx, int64_t* n_rows, int64_t* nnz);
+/* Entries held in the rows this rank owns (= indptr[n_dofs_owned]); what MatMult streams. */
+int nsgpu_owned_nnz(nsgpu_ctx* ctx, int64_t* nnz_owned);
 
 /* NonlinearPDE_SNESProblem.F (NavierStokesChannelFlow.py:51-67): forward halo of x, zero F,
  * assemble_vector(F, L), apply_lifting(F, [a], [bc], [x], -1.0), reverse halo-add, set_bc(F, bc, x, -1.0).
@@ -142,6 +144,9 @@ int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n);
 int64_t nsgpu_launch_count(nsgpu_ctx* ctx);
 /* Device time (ms) of the main kernel(s) of the last *_dev call; synchronises on that call's end event. */
 int nsgpu_last_kernel_ms(nsgpu_ctx* ctx, double* ms);
+/* CUDA-event stopwatch on ctx's stream (the stream every kernel of ctx is launched on). */
+int nsgpu_timer_start(nsgpu_ctx* ctx);
+int nsgpu_timer_stop(nsgpu_ctx* ctx, double* ms);
 
 /* ---- multi-GPU: x.ghostUpdate(INSERT, FORWARD) / F.ghostUpdate(ADD, REVERSE) / J.assemble()
  *      (NavierStokesChannelFlow.py:57-60, :66, :75) over NCCL ------------------------------------- */

@@ -1,0 +1,243 @@
+"""Host-side mirror of the reference's assembly seam, on top of the C ABI (ctypes, NumPy in/out).
+
+``NSAssembler`` owns one GPU context (= one MPI rank's partition) and exposes the five dolfinx calls the
+reference makes per Newton iterate -- ``create_matrix``, ``assemble_vector`` + ``apply_lifting`` + ``set_bc``
+(= ``residual``) and ``assemble_matrix`` (= ``jacobian``) -- plus ``mult`` (PETSc MatMult).
+``NonlinearPDE_SNESProblem`` keeps the constructor role and the ``F(snes, x, F)`` / ``J(snes, x, J, P)``
+callback signatures of NavierStokes/NavierStokesChannelFlow.py:40-75 so that ``snes.setFunction`` /
+``snes.setJacobian`` (:278-279) can be pointed at it unchanged.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+GMETRIC, UGN, STOKES = 0, 1, 2
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class NSAssembler:
+    def __init__(self, x, cells, dofmap, vdeg=1, n_dofs_owned=None, n_dofs_ghost=0, n_cells_owned=None, device=0):
+        self.lib = _lib.load()
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.nsgpu_create(ctypes.byref(self.ctx), device)
+        if rc != 0:
+            raise _lib.NsgpuError(f"nsgpu_create failed ({rc}): {self.lib.nsgpu_last_error(None).decode()}")
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
+        if x.ndim != 2 or x.shape[1] != 3:
+            raise ValueError("x must be (n_nodes, 3) like mesh.geometry.x")
+        self.gdim = cells.shape[1] - 1
+        self.vdeg = vdeg
+        self.n_cells_total = cells.shape[0]
+        self.n_cells_owned = self.n_cells_total if n_cells_owned is None else int(n_cells_owned)
+        if dofmap.shape[0] != self.n_cells_total:
+            raise ValueError("dofmap and geometry dofmap must have one row per cell")
+        self.ndofs_cell = dofmap.shape[1]
+        n_total = int(dofmap.max()) + 1 if n_dofs_owned is None else int(n_dofs_owned) + int(n_dofs_ghost)
+        self.n_owned = n_total - int(n_dofs_ghost) if n_dofs_owned is None else int(n_dofs_owned)
+        self.n_ghost = int(n_dofs_ghost)
+        self.n_dofs = self.n_owned + self.n_ghost
+        self._check(self.lib.nsgpu_set_mesh(self.ctx, self.gdim, x.shape[0], _ptr(x), self.n_cells_owned, self.n_cells_total, _ptr(cells)), "set_mesh")
+        self._check(self.lib.nsgpu_set_space(self.ctx, vdeg, _ptr(dofmap), self.n_owned, self.n_ghost), "set_space")
+        self.nnz = None
+        self.n_rows = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, what):
+        _lib.check(self.ctx, rc, what)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.nsgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        self._check(self.lib.nsgpu_set_option(self.ctx, name.encode(), int(value)), f"set_option({name})")
+
+    # ------------------------------------------------------------------ problem definition
+    def set_form(self, flavour=GMETRIC, nu=0.1, Ci=36.0, alpha=1.0, sp=1.0, beta=0.0):
+        """define_navier_stokes_form(W, msh, Re) reduced to its parameters (nu = 1/Re)."""
+        self._check(self.lib.nsgpu_set_form(self.ctx, int(flavour), float(nu), float(Ci), float(alpha), float(sp), float(beta)), "set_form")
+
+    def set_bcs(self, bcs):
+        """bcs: ordered list of (dofs, values), one pair per dirichletbc object."""
+        ptr = np.zeros(len(bcs) + 1, dtype=np.int64)
+        for k, (d, _) in enumerate(bcs):
+            ptr[k + 1] = ptr[k] + len(d)
+        dofs = np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.int32) for d, _ in bcs]) if bcs else np.zeros(0, np.int32))
+        vals = np.ascontiguousarray(np.concatenate([np.broadcast_to(np.asarray(v, dtype=np.float64), (len(d),)) for d, v in bcs]) if bcs else np.zeros(0))
+        self._check(self.lib.nsgpu_set_bcs(self.ctx, len(bcs), _ptr(ptr), _ptr(dofs), _ptr(vals)), "set_bcs")
+
+    def create_matrix(self, fetch=True):
+        """create_matrix(problem.a): returns (indptr int64, indices int32) of the CSR pattern."""
+        nnz = ctypes.c_int64()
+        self._check(self.lib.nsgpu_build_pattern(self.ctx, ctypes.byref(nnz)), "build_pattern")
+        self.nnz = nnz.value
+        self.n_rows = self.n_dofs
+        if not fetch:
+            return None
+        indptr = np.empty(self.n_rows + 1, dtype=np.int64)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        self._check(self.lib.nsgpu_get_pattern(self.ctx, _ptr(indptr), _ptr(indices)), "get_pattern")
+        return indptr, indices
+
+    def owned_nnz(self):
+        n = ctypes.c_int64()
+        self._check(self.lib.nsgpu_owned_nnz(self.ctx, ctypes.byref(n)), "owned_nnz")
+        return n.value
+
+    # ------------------------------------------------------------------ the hot path
+    def residual(self, x, out=None):
+        """F of NavierStokesChannelFlow.py:51-67 (assemble_vector + apply_lifting + reverse halo + set_bc)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty(self.n_dofs) if out is None else out
+        self._check(self.lib.nsgpu_residual(self.ctx, _ptr(x), _ptr(out)), "residual")
+        return out
+
+    def jacobian(self, x, out=None, fetch=True):
+        """J of NavierStokesChannelFlow.py:69-75.  fetch=False keeps the values on the device (MatShell)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if fetch and out is None:
+            out = np.empty(self.nnz)
+        self._check(self.lib.nsgpu_jacobian(self.ctx, _ptr(x), _ptr(out) if fetch else None), "jacobian")
+        return out
+
+    def jacobian_residual(self, x, vals_out=None, F_out=None, fetch_vals=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        F_out = np.empty(self.n_dofs) if F_out is None else F_out
+        if fetch_vals and vals_out is None:
+            vals_out = np.empty(self.nnz)
+        self._check(self.lib.nsgpu_jacobian_residual(self.ctx, _ptr(x), _ptr(vals_out) if fetch_vals else None, _ptr(F_out)), "jacobian_residual")
+        return vals_out, F_out
+
+    def mult(self, x, out=None):
+        """PETSc MatMult with the last assembled Jacobian: y_owned = J x."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty(self.n_owned) if out is None else out
+        self._check(self.lib.nsgpu_spmv(self.ctx, _ptr(x), _ptr(out)), "spmv")
+        return out
+
+    def set_values(self, vals):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self._check(self.lib.nsgpu_set_values(self.ctx, _ptr(vals)), "set_values")
+
+    def get_values(self):
+        out = np.empty(self.nnz)
+        self._check(self.lib.nsgpu_get_values(self.ctx, _ptr(out)), "get_values")
+        return out
+
+    def timers(self):
+        ms = (ctypes.c_double * 8)()
+        self._check(self.lib.nsgpu_timers(self.ctx, ms, 8), "timers")
+        keys = ["jacobian_residual", "residual", "spmv", "halo", "h2d", "d2h", "pattern", "spare"]
+        return dict(zip(keys, list(ms)))
+
+    def launch_count(self):
+        return int(self.lib.nsgpu_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ device-resident variants
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self.lib.nsgpu_dev_alloc(self.ctx, int(nbytes), ctypes.byref(p)), "dev_alloc")
+        return p
+
+    def dev_free(self, p):
+        self._check(self.lib.nsgpu_dev_free(self.ctx, p), "dev_free")
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.nsgpu_memcpy_h2d(self.ctx, dptr, _ptr(arr), arr.nbytes), "h2d")
+
+    def d2h(self, arr, dptr):
+        self._check(self.lib.nsgpu_memcpy_d2h(self.ctx, _ptr(arr), dptr, arr.nbytes), "d2h")
+
+    def jacobian_residual_dev(self, x_dev, want_jacobian=True, F_dev=None):
+        self._check(self.lib.nsgpu_jacobian_residual_dev(self.ctx, x_dev, 1 if want_jacobian else 0, F_dev), "jacobian_residual_dev")
+
+    def spmv_dev(self, x_dev, y_dev):
+        self._check(self.lib.nsgpu_spmv_dev(self.ctx, x_dev, y_dev), "spmv_dev")
+
+    def sync(self):
+        self._check(self.lib.nsgpu_sync(self.ctx), "sync")
+
+    def timer_start(self):
+        self._check(self.lib.nsgpu_timer_start(self.ctx), "timer_start")
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        self._check(self.lib.nsgpu_timer_stop(self.ctx, ctypes.byref(ms)), "timer_stop")
+        return ms.value
+
+    def pinned_empty(self, n, dtype=np.float64):
+        """NumPy array backed by page-locked host memory (cudaMallocHost)."""
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        rc = self.lib.nsgpu_host_alloc_pinned(nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise _lib.NsgpuError("cudaMallocHost failed")
+        buf = (ctypes.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_double()
+        self._check(self.lib.nsgpu_last_kernel_ms(self.ctx, ctypes.byref(ms)), "last_kernel_ms")
+        return ms.value
+
+
+def _as_array(v):
+    """NumPy view of a NumPy array or of a petsc4py Vec (``.array``)."""
+    return v if isinstance(v, np.ndarray) else v.array
+
+
+class NonlinearPDE_SNESProblem:
+    """Same role and callback signatures as the class of that name in
+    NavierStokes/NavierStokesChannelFlow.py:40-75.  ``F``/``J`` accept NumPy arrays or petsc4py objects:
+    a Vec is accessed through ``.array``; a Mat is filled with ``setValuesCSR`` when it has that method,
+    otherwise ``J`` is treated as the CSR value array itself."""
+
+    def __init__(self, assembler, u=None):
+        self.asm = assembler
+        self.u = u                       # optional mirror of the state vector (self.u of the reference)
+        self.pattern = None
+
+    def create_matrix(self):
+        self.pattern = self.asm.create_matrix()
+        return self.pattern
+
+    def F(self, snes, x, F):
+        """Assemble residual vector (x.ghostUpdate, assemble_vector, apply_lifting, F.ghostUpdate, set_bc)."""
+        xa = _as_array(x)
+        if self.u is not None:
+            _as_array(self.u)[:] = xa     # x.copy(self.u.x.petsc_vec)
+        Fa = _as_array(F)
+        res = self.asm.residual(xa)
+        Fa[: self.asm.n_owned] = res[: self.asm.n_owned]
+        if Fa.size == self.asm.n_dofs:
+            Fa[self.asm.n_owned:] = 0.0   # ghost part of F is zero after the reverse scatter
+
+    def J(self, snes, x, J, P=None):
+        """Assemble Jacobian matrix (zeroEntries, assemble_matrix with bcs, assemble)."""
+        xa = _as_array(x)
+        vals = self.asm.jacobian(xa)
+        if hasattr(J, "setValuesCSR"):
+            indptr, indices = self.pattern if self.pattern is not None else self.create_matrix()
+            n = self.asm.n_owned
+            J.zeroEntries()
+            J.setValuesCSR(indptr[: n + 1].astype(np.int32), indices[: indptr[n]], vals[: indptr[n]])
+            J.assemble()
+        else:
+            _as_array(J)[:] = vals

@@ -82,6 +82,7 @@ struct nsgpu_ctx {
 
   // timing / accounting
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t tev[2] = {nullptr, nullptr};   // user timer (nsgpu_timer_start/stop)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t launches = 0;
 

@@ -71,6 +71,8 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_xvec); cudaFree(ctx->d_F); cudaFree(ctx->d_y);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+  if (ctx->tev[0]) cudaEventDestroy(ctx->tev[0]);
+  if (ctx->tev[1]) cudaEventDestroy(ctx->tev[1]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NSGPU_OK;
@@ -195,6 +197,13 @@ int nsgpu_pattern_sizes(nsgpu_ctx* ctx, int64_t* n_rows, int64_t* nnz) {
   NS_REQUIRE(ctx, ctx->pattern_built, "pattern_sizes: call build_pattern first");
   if (n_rows) *n_rows = ctx->n_rows;
   if (nnz) *nnz = ctx->nnz;
+  return NSGPU_OK;
+}
+
+int nsgpu_owned_nnz(nsgpu_ctx* ctx, int64_t* nnz_owned) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built && nnz_owned, "owned_nnz: call build_pattern first");
+  NS_CUDA(ctx, cudaMemcpy(nnz_owned, ctx->d_indptr + ctx->n_owned, sizeof(int64_t), cudaMemcpyDeviceToHost));
   return NSGPU_OK;
 }
 
@@ -392,5 +401,23 @@ int nsgpu_last_kernel_ms(nsgpu_ctx* ctx, double* ms) {
 }
 
 int64_t nsgpu_launch_count(nsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nsgpu_timer_start(nsgpu_ctx* ctx) {
+  NS_ENTER(ctx);
+  if (!ctx->tev[0]) { NS_CUDA(ctx, cudaEventCreate(&ctx->tev[0])); NS_CUDA(ctx, cudaEventCreate(&ctx->tev[1])); }
+  NS_CUDA(ctx, cudaEventRecord(ctx->tev[0], ctx->stream));
+  return NSGPU_OK;
+}
+
+int nsgpu_timer_stop(nsgpu_ctx* ctx, double* ms) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->tev[0] && ms, "timer_stop: timer not started or NULL output");
+  NS_CUDA(ctx, cudaEventRecord(ctx->tev[1], ctx->stream));
+  NS_CUDA(ctx, cudaEventSynchronize(ctx->tev[1]));
+  float t = 0.f;
+  NS_CUDA(ctx, cudaEventElapsedTime(&t, ctx->tev[0], ctx->tev[1]));
+  *ms = t;
+  return NSGPU_OK;
+}
 
 }  // extern "C"

@@ -75,10 +75,10 @@ def create_box_tets(n, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), axes=(0, 1, 2)):
     b0, b1, b2 = np.meshgrid(np.arange(n0), np.arange(n1), np.arange(n2), indexing="ij")
     # box-major order with the first logical axis fastest
     order = np.argsort((b0 + n0 * (b1 + n1 * b2)).ravel(), kind="stable")
-    base = (b0 + s0 * b1 + s1 * b2).ravel()[order]
-    corner = np.array([(k & 1) + s0 * ((k >> 1) & 1) + s1 * ((k >> 2) & 1) for k in range(8)], dtype=np.int64)
+    base = (b0 + s0 * b1 + s1 * b2).ravel()[order].astype(np.int32)
+    corner = np.array([(k & 1) + s0 * ((k >> 1) & 1) + s1 * ((k >> 2) & 1) for k in range(8)], dtype=np.int32)
     cells = (base[:, None, None] + corner[_BOX_TETS][None, :, :]).reshape(-1, 4)
-    return Mesh(3, x, cells.astype(np.int32), (n0, n1, n2), {"kind": "box_tets", "axes": tuple(axes)})
+    return Mesh(3, x, np.ascontiguousarray(cells, dtype=np.int32), (n0, n1, n2), {"kind": "box_tets", "axes": tuple(axes)})
 
 
 def duct_mesh(n_cross, n_long, length=4.0):
@@ -110,20 +110,21 @@ def mixed_space(mesh, vdeg=1):
     """Mixed P_vdeg^gdim x P1 dof map, dolfinx cell-local ordering, entity-contiguous global numbering."""
     gd = mesh.gdim
     nv = mesh.n_vertices
-    cells = mesh.cells.astype(np.int64)
-    nc = cells.shape[0]
+    nc = mesh.cells.shape[0]
     bs = gd + 1
     if vdeg == 1:
         nvn = gd + 1
-        dm = np.empty((nc, gd * nvn + gd + 1), dtype=np.int64)
+        dm = np.empty((nc, gd * nvn + gd + 1), dtype=np.int32)
         for n in range(nvn):
+            base = bs * mesh.cells[:, n]
             for c in range(gd):
-                dm[:, gd * n + c] = bs * cells[:, n] + c
-            dm[:, gd * nvn + n] = bs * cells[:, n] + gd
+                dm[:, gd * n + c] = base + c
+            dm[:, gd * nvn + n] = base + gd
         n_dofs = bs * nv
         dof_x = np.repeat(mesh.x, bs, axis=0)
         dof_comp = np.tile(np.arange(bs, dtype=np.int8), nv)
-        return Space(mesh, 1, dm.astype(np.int32), n_dofs, dof_x, dof_comp)
+        return Space(mesh, 1, dm, n_dofs, dof_x, dof_comp)
+    cells = mesh.cells.astype(np.int64)
     ledges = TET_EDGES if gd == 3 else TRI_EDGES
     ne_l = len(ledges)
     pairs = np.sort(cells[:, ledges], axis=2)                      # (nc, ne_l, 2)

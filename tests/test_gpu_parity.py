@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on a real B200 (-m gpu).
+
+Tolerances (BASELINE.json north_star): CSR pattern and dof map bit-exact; assembled entries within 1e-12
+relative.  "Relative" is measured against the largest magnitude in the compared array (entries that cancel
+to ~0 cannot be compared against themselves)."""
+import numpy as np
+import pytest
+
+from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler, NonlinearPDE_SNESProblem
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _case(kind):
+    if kind == "duct_p1":
+        m = M.duct_mesh(6, 16); sp = M.mixed_space(m, 1)
+        return m, sp, M.duct_state(sp), M.duct_bcs(sp), dict(flavour=0, nu=0.1)
+    if kind == "duct_p1_re70":
+        m = M.duct_mesh(5, 9); sp = M.mixed_space(m, 1)
+        return m, sp, M.duct_state(sp, seed=5), M.duct_bcs(sp), dict(flavour=0, nu=1.0 / 70)
+    if kind == "duct_p2":
+        m = M.duct_mesh(3, 8); sp = M.mixed_space(m, 2)
+        return m, sp, M.duct_state(sp), M.duct_bcs(sp), dict(flavour=0, nu=0.02)
+    if kind == "cavity_ugn":
+        m = M.create_rectangle_tris(24, 24); sp = M.mixed_space(m, 1)
+        return m, sp, M.cavity_state(sp), M.cavity_bcs(sp), dict(flavour=1, nu=1.0 / 400)
+    if kind == "cavity_ugn_p2":
+        m = M.create_rectangle_tris(10, 12); sp = M.mixed_space(m, 2)
+        return m, sp, M.cavity_state(sp), M.cavity_bcs(sp), dict(flavour=1, nu=1.0 / 100)
+    if kind == "stokes_channel":
+        m = M.duct_mesh(4, 8); sp = M.mixed_space(m, 1)
+        return m, sp, M.duct_state(sp), M.duct_bcs(sp), dict(flavour=2, nu=1.0, alpha=1.0, sp=1.0, beta=0.2)
+    if kind == "stokes_duct_p2":
+        m = M.duct_mesh(3, 6); sp = M.mixed_space(m, 2)
+        return m, sp, M.duct_state(sp), M.duct_bcs(sp), dict(flavour=2, nu=1.0, alpha=1.0, sp=-1.0, beta=0.0)
+    if kind == "stokes_lid":
+        m = M.create_rectangle_tris(16, 16); sp = M.mixed_space(m, 1)
+        return m, sp, M.cavity_state(sp), M.cavity_bcs(sp), dict(flavour=2, nu=0.01, alpha=0.01, sp=1.0, beta=1.0 / 0.12)
+    raise KeyError(kind)
+
+
+CASES = ["duct_p1", "duct_p1_re70", "duct_p2", "cavity_ugn", "cavity_ugn_p2", "stokes_channel", "stokes_duct_p2", "stokes_lid"]
+
+
+def _oracle_all(oracle, m, sp, w, bcs, fk):
+    form = oracle.Form(gdim=m.gdim, vdeg=sp.vdeg, **fk)
+    marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs], [b[1] for b in bcs])
+    indptr, indices = oracle.build_pattern(sp.dofmap, sp.n_dofs)
+    vals = oracle.assemble_jacobian(form, m.x, m.cells, sp.dofmap, w, indptr, indices, marker, mult)
+    F = oracle.assemble_residual(form, m.x, m.cells, sp.dofmap, w, marker, value)
+    oracle.set_bc(F, [b[0] for b in bcs], [b[1] for b in bcs], w)
+    return indptr, indices, vals, F
+
+
+def _gpu(m, sp, bcs, fk, kernel=0):
+    asm = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=sp.vdeg)
+    asm.set_form(**fk)
+    asm.set_bcs(bcs)
+    asm.set_option("kernel", kernel)
+    return asm
+
+
+@pytest.mark.parametrize("kind", CASES)
+def test_pattern_bit_exact_and_entries_match(oracle, kind):
+    m, sp, w, bcs, fk = _case(kind)
+    indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+    asm = _gpu(m, sp, bcs, fk)
+    gp, gi = asm.create_matrix()
+    assert gp.dtype == np.int64 and gi.dtype == np.int32
+    np.testing.assert_array_equal(gp, indptr)      # bit-exact pattern
+    np.testing.assert_array_equal(gi, indices)
+    gv = asm.jacobian(w)
+    gF = asm.residual(w)
+    assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+    assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    gv2, gF2 = asm.jacobian_residual(w)              # fused pass gives the same numbers
+    assert np.abs(gv2 - vals).max() <= RTOL * np.abs(vals).max()
+    assert np.abs(gF2 - F).max() <= RTOL * np.abs(F).max()
+    # MatMult with the resident Jacobian
+    xv = np.random.default_rng(1).standard_normal(sp.n_dofs)
+    y = asm.mult(xv)
+    yo = oracle.spmv(indptr, indices, vals, xv)
+    assert np.abs(y - yo).max() <= RTOL * np.abs(yo).max()
+    asm.close()
+
+
+def test_generic_and_fast_kernels_agree(oracle):
+    m, sp, w, bcs, fk = _case("duct_p1")
+    indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+    for kernel in (1, 0):
+        asm = _gpu(m, sp, bcs, fk, kernel)
+        asm.create_matrix(fetch=False)
+        gv, gF = asm.jacobian_residual(w)
+        assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+        assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+        asm.close()
+
+
+def test_lifting_with_state_off_the_dirichlet_values(oracle):
+    """First fine-mesh iterate: x does not satisfy the BCs, so apply_lifting contributes."""
+    m, sp, w, bcs, fk = _case("duct_p1_re70")
+    w = w + 0.05 * np.random.default_rng(2).standard_normal(sp.n_dofs)
+    _, _, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix(fetch=False)
+    gF = asm.residual(w)
+    assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    asm.close()
+
+
+def test_arbitrary_dof_numbering(oracle):
+    """dolfinx renumbers dofs (reverse Cuthill-McKee): nothing may depend on entity-contiguous numbering."""
+    m, sp, w, bcs, fk = _case("duct_p1_re70")
+    perm = np.random.default_rng(3).permutation(sp.n_dofs).astype(np.int32)
+    dofmap = perm[sp.dofmap]
+    w2 = np.empty_like(w); w2[perm] = w
+    bcs2 = [(perm[d], v) for d, v in bcs]
+    form = oracle.Form(gdim=3, vdeg=1, **fk)
+    marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs2], [b[1] for b in bcs2])
+    indptr, indices = oracle.build_pattern(dofmap, sp.n_dofs)
+    vals = oracle.assemble_jacobian(form, m.x, m.cells, dofmap, w2, indptr, indices, marker, mult)
+    asm = NSAssembler(m.x, m.cells, dofmap, vdeg=1)
+    asm.set_form(**fk); asm.set_bcs(bcs2)
+    gp, gi = asm.create_matrix()
+    np.testing.assert_array_equal(gp, indptr)
+    np.testing.assert_array_equal(gi, indices)
+    gv = asm.jacobian(w2)
+    assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+    asm.close()
+
+
+def test_reynolds_sweep_without_rebuild(oracle):
+    """run_all_RE.sh sweeps Re on one mesh: set_form may change nu without touching the pattern."""
+    m, sp, w, bcs, fk = _case("duct_p1_re70")
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix(fetch=False)
+    for Re in (40, 50, 60, 70):
+        fk2 = dict(flavour=0, nu=1.0 / Re)
+        asm.set_form(**fk2)
+        _, _, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk2)
+        gv, gF = asm.jacobian_residual(w)
+        assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+        assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    asm.close()
+
+
+def test_snes_callback_mirror(oracle):
+    """NonlinearPDE_SNESProblem.F/J keep the reference signatures (snes, x, F) / (snes, x, J, P)."""
+    m, sp, w, bcs, fk = _case("duct_p1_re70")
+    _, _, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+    asm = _gpu(m, sp, bcs, fk)
+    prob = NonlinearPDE_SNESProblem(asm, u=np.zeros(sp.n_dofs))
+    indptr, indices = prob.create_matrix()
+    b = np.zeros(sp.n_dofs); Jv = np.zeros(len(indices))
+    prob.F(None, w, b)
+    prob.J(None, w, Jv, None)
+    assert np.abs(b - F).max() <= RTOL * np.abs(F).max()
+    assert np.abs(Jv - vals).max() <= RTOL * np.abs(vals).max()
+    np.testing.assert_array_equal(prob.u, w)
+    asm.close()
+
+
+def test_size_independent_properties_at_scale():
+    """At a size the oracle cannot finish quickly (3 M cells): linear-state patch property, row sums,
+    and determinism of the scatter up to summation order."""
+    m = M.duct_mesh(50, 200); sp = M.mixed_space(m, 1)
+    asm = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=1)
+    asm.set_form(flavour=0, nu=0.1)
+    indptr, indices = asm.create_matrix()
+    assert len(indices) == 122534416                      # SURVEY A.6 closed form
+    # constant state => interior residual rows vanish (patch test)
+    w = np.zeros(sp.n_dofs)
+    for c, v in enumerate((0.7, -0.3, 0.2, 1.9)):
+        w[sp.dof_comp == c] = v
+    F = asm.residual(w)
+    X = sp.dof_x
+    interior = (X[:, 0] > 1e-9) & (X[:, 0] < 4 - 1e-9) & (np.abs(X[:, 1]) < 0.5 - 1e-9) & (np.abs(X[:, 2]) < 0.5 - 1e-9)
+    assert np.abs(F[interior]).max() < 1e-13
+    # J applied to the state it was linearised at reproduces the Stokes part: check J*1_p = 0 rows for
+    # velocity-velocity block is not generally zero, so use two assemblies: identical up to summation order
+    ws = M.duct_state(sp)
+    v1 = asm.jacobian(ws); v2 = asm.jacobian(ws)
+    assert np.abs(v1 - v2).max() <= 1e-14 * np.abs(v1).max()
+    # MatMult linearity
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(sp.n_dofs), rng.standard_normal(sp.n_dofs)
+    ya, yb, yab = asm.mult(a), asm.mult(b), asm.mult(2 * a - 3 * b)
+    assert np.abs(yab - (2 * ya - 3 * yb)).max() <= 1e-12 * np.abs(yab).max()
+    asm.close()
