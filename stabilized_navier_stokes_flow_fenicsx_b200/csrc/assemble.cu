@@ -103,17 +103,20 @@ static void launch_generic(nsgpu_ctx* ctx, const double* d_xin, bool want_J, boo
 // d_xin: n_dofs state (halo already refreshed).  d_Fout: n_dofs residual (zeroed here).
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   cudaStream_t s = ctx->stream;
-  if (want_J) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));   // J.zeroEntries()
-  if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_dofs, s));                          // f_local.set(0.0)
-  NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
-
   bool fast = false;
   if (ctx->gdim == 3 && ctx->vdeg == 1 && ctx->form.flavour == NSGPU_FORM_GMETRIC && ctx->kernel_sel != NSGPU_KERNEL_GENERIC)
     fast = p1tet_fast_available(ctx);
   if (ctx->kernel_sel == NSGPU_KERNEL_FAST && !fast) {
-    set_error(ctx, "kernel=fast requested but the factorised kernel does not apply to this element/form");
+    set_error(ctx, "kernel=fast requested but the factorised kernel does not apply to this element/form/numbering");
     return NSGPU_EUNSUPPORTED;
   }
+  // J.zeroEntries(): the row-owner kernel writes every entry of every locally assembled row exactly once, so the
+  // zero-fill pass is only needed when rows also hold entries that only other ranks contribute to.
+  const bool zero_vals = want_J && !(fast && ctx->extra_rows.empty());
+  if (zero_vals) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));
+  if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_dofs, s));                          // f_local.set(0.0)
+  NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+
   if (fast) {
     int rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout);
     if (rc != NSGPU_OK) return rc;

@@ -70,6 +70,14 @@ struct nsgpu_ctx {
   uint16_t* d_rel = nullptr;    // [cell][entity][local col] rank of the column inside the entity's rows
   int64_t* d_diag = nullptr;    // position of (i,i) per row, -1 if absent
   std::vector<int32_t> extra_rows, extra_cols;  // pattern entries received from other ranks
+  // entity-level structure kept from the pattern build (entity = dofs of one vertex / edge, named by its first dof)
+  uint64_t* d_pairs = nullptr;      // sorted unique (A << 32 | B) entity pairs
+  int64_t n_pairs = 0;
+  int64_t* d_pair_first = nullptr;  // per leader dof: first / one-past-last pair of its row group (-1 if none)
+  int64_t* d_pair_last = nullptr;
+  int32_t* d_members = nullptr;     // [leader dof][KMAX] member dofs
+  bool rows_presorted = false;      // column blocks of each row are contiguous per neighbour entity, in pair order
+  struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
 
   // work vectors (n_dofs)
   double* d_xvec = nullptr;

@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "element_p1tet.cuh"
 
 using namespace nsgpu;
 
@@ -69,6 +70,8 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_bc_marker); cudaFree(ctx->d_bc_value); cudaFree(ctx->d_bc_mult);
   cudaFree(ctx->d_indptr); cudaFree(ctx->d_indices); cudaFree(ctx->d_vals); cudaFree(ctx->d_rel); cudaFree(ctx->d_diag);
   cudaFree(ctx->d_xvec); cudaFree(ctx->d_F); cudaFree(ctx->d_y);
+  cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
+  p1tet_free(ctx);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   if (ctx->tev[0]) cudaEventDestroy(ctx->tev[0]);
@@ -155,6 +158,7 @@ int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr, const int32_t
     }
   }
   ctx->has_bc = total > 0;
+  p1tet_mark_bc_dirty(ctx);
   NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_marker, marker.data(), ctx->n_dofs, cudaMemcpyHostToDevice));
   NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_value, value.data(), sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice));
   NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_mult, mult.data(), sizeof(int32_t) * ctx->n_dofs, cudaMemcpyHostToDevice));

@@ -12,6 +12,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "element_p1tet.cuh"
 
 namespace nsgpu {
 
@@ -311,6 +312,13 @@ int build_pattern_impl(nsgpu_ctx* ctx) {
   PB_CUDA(cudaStreamSynchronize(s));
   PB_CUDA(cudaGetLastError());
   ctx->launches += 2;
+  // hand the entity-level structure to the context: the factorised kernels' plan is built from it
+  cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
+  ctx->d_pairs = d_keys; ctx->d_pair_first = d_first; ctx->d_pair_last = d_last; ctx->d_members = d_members;
+  ctx->n_pairs = np;
+  ctx->rows_presorted = !unsorted;
+  d_keys = nullptr; d_first = nullptr; d_last = nullptr; d_members = nullptr;
+  p1tet_free(ctx);   // any previous plan refers to the old pattern
   cleanup();
   if (bad) {
     set_error(ctx, "build_pattern: a cell dof is missing from its row, or a row holds more than 65535 entries");

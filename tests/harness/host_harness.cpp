@@ -28,3 +28,31 @@ extern "C" int harness_element_generic(int flavour, int gdim, int vdeg, double n
   else return -1;
   return 0;
 }
+
+#include "element_p1tet.cuh"
+
+// Full 16x16 element Jacobian / residual rebuilt from the four vertex row-slabs of the factorised kernel
+// (each slab is computed with its row vertex rotated to the front, exactly as the CUDA kernel does).
+extern "C" int harness_p1tet(double nu, double Ci, const double* x, const double* w, double* Ae, double* be) {
+  FormParams f{0, nu, Ci, 1.0, 1.0, 0.0};
+  for (int m = 0; m < 4; ++m) {
+    int perm[4] = {m, 0, 0, 0};
+    for (int k = 0, j = 1; k < 4; ++k) if (k != m) perm[j++] = k;
+    double xx[4][3], uu[4][3], pp[4], blk[4][16], fr[4];
+    for (int a = 0; a < 4; ++a) {
+      for (int i = 0; i < 3; ++i) { xx[a][i] = x[3 * perm[a] + i]; uu[a][i] = w[3 * perm[a] + i]; }
+      pp[a] = w[12 + perm[a]];
+    }
+    p1tet_rowslab<true, true>(f, m == 0, xx, uu, pp, blk, fr);
+    for (int r = 0; r < 4; ++r) {
+      const int row = r < 3 ? 3 * m + r : 12 + m;
+      be[row] = fr[r];
+      for (int a = 0; a < 4; ++a)
+        for (int d = 0; d < 4; ++d) {
+          const int col = d < 3 ? 3 * perm[a] + d : 12 + perm[a];
+          Ae[row * 16 + col] = blk[a][4 * r + d];
+        }
+    }
+  }
+  return 0;
+}
