@@ -165,6 +165,8 @@ def run_ours(args):
     asm.set_bcs(part.bcs)
     if args.kernel is not None:
         asm.set_option("kernel", args.kernel)
+    if args.threads is not None:
+        asm.set_option("threads", args.threads)
     D.attach(asm, part, comm)                                       # NCCL communicator + halo / ghost-row plans
     asm.create_matrix(fetch=False)
     D.finish_pattern_exchange(asm, part, comm)
@@ -287,6 +289,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NSGPU_WORKLOAD", "L"), choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=None, help="0 auto, 1 generic, 2 fast")
+    ap.add_argument("--threads", type=int, default=None, help="incidences per CTA of the factorised kernel: 128, 192, 256")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -134,7 +134,7 @@ int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_
 int nsgpu_host_alloc_pinned(int64_t bytes, void** out);
 int nsgpu_host_free_pinned(void* p);
 
-/* Options: "kernel" (NSGPU_KERNEL_*), "threads" (block size of the assembly kernels). */
+/* Options: "kernel" (NSGPU_KERNEL_*), "threads" (incidences per CTA of the factorised kernel: 128, 192 or 256). */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.

@@ -86,7 +86,7 @@ struct nsgpu_ctx {
 
   // options
   int kernel_sel = NSGPU_KERNEL_AUTO;
-  int threads = 128;
+  int threads = 128;   // incidences per CTA of the row-owner kernel: 128 (2 CTAs/SM), 192 or 256 (1 CTA/SM)
 
   // timing / accounting
   cudaEvent_t ev[2] = {nullptr, nullptr};

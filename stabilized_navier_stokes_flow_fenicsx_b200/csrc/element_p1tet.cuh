@@ -17,6 +17,12 @@
 
 namespace nsgpu {
 
+#if defined(__CUDA_ARCH__)
+#define NS_RSQRT(x) rsqrt(x)
+#else
+#define NS_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
 constexpr double P1T_A = 0.1381966011250105;   // (5 - sqrt 5) / 20
 constexpr double P1T_E = 0.4472135954999579;   // b - a = sqrt(5) / 5
 
@@ -101,7 +107,7 @@ NS_HD void p1tet_rowslab(const FormParams& fp, const bool row_is_origin, const d
       Guq[q][i] = G[i][0] * uq[q][0] + G[i][1] * uq[q][1] + G[i][2] * uq[q][2];
       arg += uq[q][i] * Guq[q][i];
     }
-    const double tau = 1.0 / sqrt(arg);           // tau_SUPS (:238)
+    const double tau = NS_RSQRT(arg);             // tau_SUPS (:238)
     const double wtau = W * tau;
     nuLbar += wtau * arg;                          // W nu_L = W sqrt(arg) / trG = W tau arg / trG (scaled below)
     // r = dot(u, grad u) + grad p  (res_M for P1: -div sigma = grad p)

@@ -377,7 +377,7 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: kernel must be 0 (auto), 1 (generic) or 2 (fast)");
     ctx->kernel_sel = (int)value;
   } else if (!strcmp(name, "threads")) {
-    NS_REQUIRE(ctx, value >= 32 && value <= 1024 && value % 32 == 0, "set_option: threads must be a multiple of 32 in [32,1024]");
+    NS_REQUIRE(ctx, value == 128 || value == 192 || value == 256, "set_option: threads must be 128, 192 or 256");
     ctx->threads = (int)value;
   } else {
     set_error(ctx, std::string("set_option: unknown option ") + name);
