@@ -167,14 +167,15 @@ def run_ours(args):
         asm.set_option("kernel", args.kernel)
     if args.threads is not None:
         asm.set_option("threads", args.threads)
-    D.attach(asm, part, comm)                                       # NCCL communicator + halo / ghost-row plans
-    asm.create_matrix(fetch=False)
-    D.finish_pattern_exchange(asm, part, comm)
+    D.attach(asm, part, comm)                                       # the library's own NCCL communicator
+    D.finish_pattern_exchange(asm, part, comm)                      # pattern (+ SparsityPattern.finalize exchange), halo / ghost-row plans
     setup_s = time.perf_counter() - t_setup
 
-    nbytes = 8 * asm.n_dofs
+    nbytes = 8 * asm.n_cols                                         # owned + ghost + column-ghost entries
     x_dev, F_dev, y_dev = asm.dev_alloc(nbytes), asm.dev_alloc(nbytes), asm.dev_alloc(nbytes)
-    asm.h2d(x_dev, part.w)
+    w_local = np.zeros(asm.n_cols)
+    w_local[: asm.n_dofs] = part.w
+    asm.h2d(x_dev, w_local)
 
     def step():
         asm.jacobian_residual_dev(x_dev, True, F_dev)

@@ -164,6 +164,18 @@ int nsgpu_set_row_exchange(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_ran
 /* Extra (row, col) entries contributed by other ranks' ghost rows (dolfinx SparsityPattern::finalize);
  * must be called before nsgpu_build_pattern. */
 int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, const int32_t* cols);
+/* Column ghosts that are dofs of no local cell but appear in rows this rank owns through other ranks' ghost
+ * rows (dolfinx SparsityPattern::finalize appends them to the column index map).  They get local column
+ * indices n_owned + n_ghost + k.  leader_local / slot / size describe which of them live on one mesh entity
+ * (leader = local index of the entity's first dof, slot = position in the entity, size = dofs on it).
+ * After this call every x_local vector has n_owned + n_ghost + n_extra entries (nsgpu_local_sizes). */
+int nsgpu_set_col_ghosts(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_local, const int32_t* slot, const int32_t* size);
+int nsgpu_local_sizes(nsgpu_ctx* ctx, int64_t* n_owned, int64_t* n_ghost, int64_t* n_cols);
+/* Rows of the pattern by local row index (used to build the J.assemble() plan without fetching the whole
+ * pattern): start_out[k] = position of the row's first entry in the CSR arrays, ptr_out has n+1 offsets into
+ * idx_out; idx_out == NULL only fills start_out / ptr_out (size query). */
+int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* start_out, int64_t* ptr_out, int32_t* idx_out,
+                   int64_t idx_capacity);
 
 #ifdef __cplusplus
 }

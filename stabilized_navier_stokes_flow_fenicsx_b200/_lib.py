@@ -62,6 +62,9 @@ SIGNATURES = {
     "nsgpu_comm_init": (ctypes.c_int, [c_ctx, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "nsgpu_set_halo": (ctypes.c_int, [c_ctx, ctypes.c_int] + [ctypes.c_void_p] * 5),
     "nsgpu_set_row_exchange": (ctypes.c_int, [c_ctx, ctypes.c_int] + [ctypes.c_void_p] * 5),
+    "nsgpu_set_col_ghosts": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nsgpu_local_sizes": (ctypes.c_int, [c_ctx, c_i64p, c_i64p, c_i64p]),
+    "nsgpu_get_rows": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "nsgpu_add_pattern_entries": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
 }
 

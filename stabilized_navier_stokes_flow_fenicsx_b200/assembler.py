@@ -45,6 +45,7 @@ class NSAssembler:
         self.n_dofs = self.n_owned + self.n_ghost
         self._check(self.lib.nsgpu_set_mesh(self.ctx, self.gdim, x.shape[0], _ptr(x), self.n_cells_owned, self.n_cells_total, _ptr(cells)), "set_mesh")
         self._check(self.lib.nsgpu_set_space(self.ctx, vdeg, _ptr(dofmap), self.n_owned, self.n_ghost), "set_space")
+        self.n_cols = self.n_dofs
         self.nnz = None
         self.n_rows = None
 
@@ -92,6 +93,56 @@ class NSAssembler:
         indices = np.empty(self.nnz, dtype=np.int32)
         self._check(self.lib.nsgpu_get_pattern(self.ctx, _ptr(indptr), _ptr(indices)), "get_pattern")
         return indptr, indices
+
+    # ------------------------------------------------------------------ multi-GPU set-up hooks (distributed.py)
+    def build_pattern(self, extra_rows=None, extra_cols=None, colx_leader=None, colx_slot=None, colx_size=None):
+        """(Re)build the pattern; the optional arguments are what other ranks' ghost rows add to rows this rank owns."""
+        nx = 0 if colx_leader is None else len(colx_leader)
+        la = np.ascontiguousarray(colx_leader if nx else np.zeros(0), dtype=np.int32)
+        sl = np.ascontiguousarray(colx_slot if nx else np.zeros(0), dtype=np.int32)
+        sz = np.ascontiguousarray(colx_size if nx else np.zeros(0), dtype=np.int32)
+        self._check(self.lib.nsgpu_set_col_ghosts(self.ctx, nx, _ptr(la), _ptr(sl), _ptr(sz)), "set_col_ghosts")
+        self.n_cols = self.n_dofs + nx
+        if extra_rows is not None and len(extra_rows):
+            er = np.ascontiguousarray(extra_rows, dtype=np.int32)
+            ec = np.ascontiguousarray(extra_cols, dtype=np.int32)
+            self._check(self.lib.nsgpu_add_pattern_entries(self.ctx, len(er), _ptr(er), _ptr(ec)), "add_pattern_entries")
+        self.create_matrix(fetch=False)
+
+    def get_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        n = len(rows)
+        start = np.zeros(n, dtype=np.int64)
+        ptr = np.zeros(n + 1, dtype=np.int64)
+        self._check(self.lib.nsgpu_get_rows(self.ctx, n, _ptr(rows), _ptr(start), _ptr(ptr), None, 0), "get_rows")
+        idx = np.zeros(int(ptr[-1]), dtype=np.int32)
+        self._check(self.lib.nsgpu_get_rows(self.ctx, n, _ptr(rows), _ptr(start), _ptr(ptr), _ptr(idx), len(idx)), "get_rows")
+        return start, ptr, idx
+
+    def comm_init(self, rank, size, unique_id):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.nsgpu_comm_init(self.ctx, rank, size, buf), "comm_init")
+
+    @staticmethod
+    def comm_unique_id():
+        lib = _lib.load()
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.nsgpu_comm_unique_id(buf, 128)
+        if rc != 0:
+            raise _lib.NsgpuError("nsgpu_comm_unique_id failed: " + lib.nsgpu_last_error(None).decode())
+        return buf.raw
+
+    def set_halo(self, neigh, send_ptr, send_idx, recv_ptr, recv_idx):
+        a = [np.ascontiguousarray(neigh, dtype=np.int32), np.ascontiguousarray(send_ptr, dtype=np.int64),
+             np.ascontiguousarray(send_idx, dtype=np.int32), np.ascontiguousarray(recv_ptr, dtype=np.int64),
+             np.ascontiguousarray(recv_idx, dtype=np.int32)]
+        self._check(self.lib.nsgpu_set_halo(self.ctx, len(a[0]), *[_ptr(v) for v in a]), "set_halo")
+
+    def set_row_exchange(self, neigh, send_ptr, send_pos, recv_ptr, recv_pos):
+        a = [np.ascontiguousarray(neigh, dtype=np.int32), np.ascontiguousarray(send_ptr, dtype=np.int64),
+             np.ascontiguousarray(send_pos, dtype=np.int64), np.ascontiguousarray(recv_ptr, dtype=np.int64),
+             np.ascontiguousarray(recv_pos, dtype=np.int64)]
+        self._check(self.lib.nsgpu_set_row_exchange(self.ctx, len(a[0]), *[_ptr(v) for v in a]), "set_row_exchange")
 
     def owned_nnz(self):
         n = ctypes.c_int64()

@@ -100,7 +100,7 @@ static void launch_generic(nsgpu_ctx* ctx, const double* d_xin, bool want_J, boo
   ctx->launches += 1;
 }
 
-// d_xin: n_dofs state (halo already refreshed).  d_Fout: n_dofs residual (zeroed here).
+// d_xin: n_cols state (halo already refreshed).  d_Fout: n_cols residual (zeroed here; owned part meaningful).
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   cudaStream_t s = ctx->stream;
   bool fast = false;
@@ -114,7 +114,7 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   // zero-fill pass is only needed when rows also hold entries that only other ranks contribute to.
   const bool zero_vals = want_J && !(fast && ctx->extra_rows.empty());
   if (zero_vals) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));
-  if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_dofs, s));                          // f_local.set(0.0)
+  if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_cols, s));                          // f_local.set(0.0)
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
 
   if (fast) {

@@ -49,6 +49,8 @@ struct nsgpu_ctx {
   // space (nsgpu_set_space)
   int vdeg = 0, nd = 0, nent = 0;
   int64_t n_owned = 0, n_ghost = 0, n_dofs = 0;
+  int64_t n_cols = 0;           // n_dofs + column ghosts that only appear through other ranks' ghost rows
+  std::vector<int32_t> colx_leader, colx_slot, colx_size;   // entity structure of those extra column dofs
   int32_t* d_dofmap = nullptr;  // n_cells_total x nd
 
   // form

@@ -112,6 +112,9 @@ int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_d
   const int nvn = vdeg == 1 ? gd + 1 : (gd == 3 ? 10 : 6);
   ctx->vdeg = vdeg; ctx->nd = gd * nvn + gd + 1; ctx->nent = nvn;
   ctx->n_owned = n_dofs_owned; ctx->n_ghost = n_dofs_ghost; ctx->n_dofs = n_dofs_owned + n_dofs_ghost;
+  ctx->n_cols = ctx->n_dofs;
+  ctx->colx_leader.clear(); ctx->colx_slot.clear(); ctx->colx_size.clear();
+  ctx->extra_rows.clear(); ctx->extra_cols.clear();
   ctx->pattern_built = false;
   ctx->has_bc = false;
   int rc;
@@ -169,11 +172,62 @@ int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, co
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, n >= 0 && (n == 0 || (rows && cols)), "add_pattern_entries: NULL arrays");
   for (int64_t k = 0; k < n; ++k) {
-    NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_dofs && cols[k] >= 0 && cols[k] < ctx->n_dofs, "add_pattern_entries: index out of range");
+    NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_dofs && cols[k] >= 0 && cols[k] < ctx->n_cols, "add_pattern_entries: index out of range");
   }
   ctx->extra_rows.insert(ctx->extra_rows.end(), rows, rows + n);
   ctx->extra_cols.insert(ctx->extra_cols.end(), cols, cols + n);
   ctx->pattern_built = false;
+  return NSGPU_OK;
+}
+
+int nsgpu_set_col_ghosts(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_local, const int32_t* slot, const int32_t* size) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->n_dofs > 0, "set_col_ghosts: call set_space first");
+  NS_REQUIRE(ctx, n_extra >= 0 && (n_extra == 0 || (leader_local && slot && size)), "set_col_ghosts: NULL arrays");
+  NS_REQUIRE(ctx, ctx->n_dofs + n_extra < (int64_t)2147483647, "set_col_ghosts: local column count exceeds int32");
+  for (int64_t k = 0; k < n_extra; ++k) {
+    NS_REQUIRE(ctx, leader_local[k] >= ctx->n_dofs && leader_local[k] < ctx->n_dofs + n_extra && slot[k] >= 0 && slot[k] < KMAX &&
+                        size[k] >= 1 && size[k] <= KMAX, "set_col_ghosts: bad entity description");
+  }
+  ctx->n_cols = ctx->n_dofs + n_extra;
+  ctx->colx_leader.assign(leader_local, leader_local + n_extra);
+  ctx->colx_slot.assign(slot, slot + n_extra);
+  ctx->colx_size.assign(size, size + n_extra);
+  ctx->pattern_built = false;
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_xvec, ctx->n_cols))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_y, ctx->n_cols))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_F, ctx->n_cols))) return rc;
+  NS_CUDA(ctx, cudaMemset(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols));
+  return NSGPU_OK;
+}
+
+int nsgpu_local_sizes(nsgpu_ctx* ctx, int64_t* n_owned, int64_t* n_ghost, int64_t* n_cols) {
+  NS_ENTER(ctx);
+  if (n_owned) *n_owned = ctx->n_owned;
+  if (n_ghost) *n_ghost = ctx->n_ghost;
+  if (n_cols) *n_cols = ctx->n_cols;
+  return NSGPU_OK;
+}
+
+int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* start_out, int64_t* ptr_out, int32_t* idx_out, int64_t idx_capacity) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "get_rows: call build_pattern first");
+  NS_REQUIRE(ctx, n >= 0 && (n == 0 || (rows && ptr_out)), "get_rows: NULL arrays");
+  std::vector<int64_t> b(n), e(n);
+  ptr_out[0] = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_rows, "get_rows: row out of range");
+    int64_t be[2];
+    NS_CUDA(ctx, cudaMemcpy(be, ctx->d_indptr + rows[k], 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    b[k] = be[0]; e[k] = be[1];
+    if (start_out) start_out[k] = be[0];
+    ptr_out[k + 1] = ptr_out[k] + (be[1] - be[0]);
+  }
+  if (!idx_out) return NSGPU_OK;   // size query
+  NS_REQUIRE(ctx, idx_capacity >= ptr_out[n], "get_rows: idx_out too small");
+  for (int64_t k = 0; k < n; ++k)
+    if (e[k] > b[k]) NS_CUDA(ctx, cudaMemcpy(idx_out + ptr_out[k], ctx->d_indices + b[k], sizeof(int32_t) * (e[k] - b[k]), cudaMemcpyDeviceToHost));
   return NSGPU_OK;
 }
 

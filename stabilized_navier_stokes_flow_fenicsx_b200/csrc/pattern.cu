@@ -62,6 +62,17 @@ __global__ void k_entity_tables(int64_t n_cells, int nd, EntityLayout L, const i
   }
 }
 
+// column ghosts that are not dofs of any local cell: entity structure supplied by the host
+__global__ void k_extra_entities(int64_t nx, int64_t n_dofs, const int32_t* __restrict__ lead, const int32_t* __restrict__ slot,
+                                 const int32_t* __restrict__ size, int32_t* leader, int32_t* members, uint8_t* esize) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nx) return;
+  const int64_t d = n_dofs + k;
+  leader[d] = lead[k];
+  members[(int64_t)lead[k] * KMAX + slot[k]] = (int32_t)d;
+  esize[lead[k]] = (uint8_t)size[k];
+}
+
 __global__ void k_pair_keys(int64_t n_cells, int nd, EntityLayout L, const int32_t* __restrict__ dofmap, uint64_t* keys) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int n2 = L.nent * L.nent;
@@ -182,7 +193,8 @@ int build_pattern_impl(nsgpu_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   const int gd = ctx->gdim, nd = ctx->nd;
   const EntityLayout L = make_layout(gd, ctx->vdeg);
-  const int64_t n_dofs = ctx->n_dofs;
+  const int64_t n_dofs = ctx->n_dofs;     // rows
+  const int64_t n_cols = ctx->n_cols;     // columns (>= n_dofs on ranks that own rows other ranks contribute to)
   ctx->n_rows = n_dofs;  // owned + ghost rows are kept locally (dolfinx la::MatrixCSR layout)
 
   int32_t *d_leader = nullptr, *d_members = nullptr;
@@ -207,14 +219,26 @@ int build_pattern_impl(nsgpu_ctx* ctx) {
     }                                                                                               \
   } while (0)
 
-  PB_CUDA(cudaMalloc(&d_leader, sizeof(int32_t) * n_dofs));
-  PB_CUDA(cudaMalloc(&d_members, sizeof(int32_t) * n_dofs * KMAX));
-  PB_CUDA(cudaMalloc(&d_esize, n_dofs));
+  PB_CUDA(cudaMalloc(&d_leader, sizeof(int32_t) * n_cols));
+  PB_CUDA(cudaMalloc(&d_members, sizeof(int32_t) * n_cols * KMAX));
+  PB_CUDA(cudaMalloc(&d_esize, n_cols));
   PB_CUDA(cudaMalloc(&d_flag, sizeof(int)));
   PB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
-  k_init_leader<<<grid_for(n_dofs), 256, 0, s>>>(n_dofs, d_leader, d_esize);
+  k_init_leader<<<grid_for(n_cols), 256, 0, s>>>(n_cols, d_leader, d_esize);
   k_entity_tables<<<grid_for(ctx->n_cells_total * L.nent), 256, 0, s>>>(ctx->n_cells_total, nd, L, ctx->d_dofmap, d_leader, d_members, d_esize);
   ctx->launches += 2;
+  if (n_cols > n_dofs) {
+    const int64_t nx = n_cols - n_dofs;
+    int32_t* d_x3 = nullptr;
+    PB_CUDA(cudaMalloc(&d_x3, sizeof(int32_t) * 3 * nx));
+    PB_CUDA(cudaMemcpyAsync(d_x3, ctx->colx_leader.data(), sizeof(int32_t) * nx, cudaMemcpyHostToDevice, s));
+    PB_CUDA(cudaMemcpyAsync(d_x3 + nx, ctx->colx_slot.data(), sizeof(int32_t) * nx, cudaMemcpyHostToDevice, s));
+    PB_CUDA(cudaMemcpyAsync(d_x3 + 2 * nx, ctx->colx_size.data(), sizeof(int32_t) * nx, cudaMemcpyHostToDevice, s));
+    k_extra_entities<<<grid_for(nx), 256, 0, s>>>(nx, n_dofs, d_x3, d_x3 + nx, d_x3 + 2 * nx, d_leader, d_members, d_esize);
+    PB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_x3);
+    ctx->launches += 1;
+  }
 
   // (entity, entity) keys of owned cells + entries shipped from other ranks' ghost rows
   const int64_t n_extra = (int64_t)ctx->extra_rows.size();
@@ -237,7 +261,7 @@ int build_pattern_impl(nsgpu_ctx* ctx) {
 
   // sort + unique
   int key_bits = 32;
-  while (key_bits > 1 && !((uint64_t)(n_dofs - 1) >> (key_bits - 1))) --key_bits;
+  while (key_bits > 1 && !((uint64_t)(n_cols - 1) >> (key_bits - 1))) --key_bits;
   size_t tmp_bytes = 0;
   PB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, n_keys, 0, 32 + key_bits, s));
   PB_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
@@ -258,10 +282,10 @@ int build_pattern_impl(nsgpu_ctx* ctx) {
   // per-pair widths -> offsets inside the entity rows
   PB_CUDA(cudaMalloc(&d_w, sizeof(int64_t) * (np + 1)));
   PB_CUDA(cudaMalloc(&d_woff, sizeof(int64_t) * (np + 1)));
-  PB_CUDA(cudaMalloc(&d_first, sizeof(int64_t) * n_dofs));
-  PB_CUDA(cudaMalloc(&d_last, sizeof(int64_t) * n_dofs));
-  PB_CUDA(cudaMemsetAsync(d_first, 0xff, sizeof(int64_t) * n_dofs, s));
-  PB_CUDA(cudaMemsetAsync(d_last, 0xff, sizeof(int64_t) * n_dofs, s));
+  PB_CUDA(cudaMalloc(&d_first, sizeof(int64_t) * n_cols));
+  PB_CUDA(cudaMalloc(&d_last, sizeof(int64_t) * n_cols));
+  PB_CUDA(cudaMemsetAsync(d_first, 0xff, sizeof(int64_t) * n_cols, s));
+  PB_CUDA(cudaMemsetAsync(d_last, 0xff, sizeof(int64_t) * n_cols, s));
   k_pair_weight<<<grid_for(np + 1), 256, 0, s>>>(np, d_keys, d_esize, d_w);
   tmp_bytes = 0;
   PB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_w, d_woff, np + 1, s));

@@ -187,14 +187,181 @@ def duct_partition(n_cross, n_long, rank, size, length=4.0, seed=1234, noise=1e-
 
 
 # ------------------------------------------------------------------------------------------------ plans
+def entity_tables(dofmap, gdim, vdeg, n_dofs):
+    """leader / slot / size of every local dof: dofs on one mesh entity (vertex: gdim velocity components +
+    pressure; P2 edge: gdim components) share their cell incidence -- same grouping as csrc/pattern.cu."""
+    nv = gdim + 1
+    ne = 0 if vdeg == 1 else (6 if gdim == 3 else 3)
+    poff = gdim * (nv + ne)
+    leader = np.arange(n_dofs, dtype=np.int64)
+    slot = np.zeros(n_dofs, dtype=np.int64)
+    size = np.ones(n_dofs, dtype=np.int64)
+    dm = np.asarray(dofmap, dtype=np.int64)
+    for n in range(nv):
+        lead = dm[:, gdim * n]
+        for c in range(gdim):
+            d = dm[:, gdim * n + c]
+            leader[d], slot[d], size[d] = lead, c, gdim + 1
+        d = dm[:, poff + n]
+        leader[d], slot[d], size[d] = lead, gdim, gdim + 1
+    for e in range(ne):
+        lead = dm[:, gdim * (nv + e)]
+        for c in range(gdim):
+            d = dm[:, gdim * (nv + e) + c]
+            leader[d], slot[d], size[d] = lead, c, gdim
+    return leader, slot, size
+
+
+@dataclass
+class Plans:
+    n_cols: int
+    col_ghost_global: np.ndarray        # global index of the column ghosts appended after the dofmap ghosts
+    col_ghost_owner: np.ndarray
+    halo: tuple                         # (neigh, send_ptr, send_idx, recv_ptr, recv_idx)
+    rows: tuple                         # (neigh, send_ptr, send_pos, recv_ptr, recv_pos)
+    extra: tuple                        # (extra_rows, extra_cols, colx_leader, colx_slot, colx_size)
+
+
+def _group(ranks):
+    """stable grouping: returns {rank: index array} in ascending rank order."""
+    out = {}
+    for r in np.unique(ranks):
+        out[int(r)] = np.nonzero(ranks == r)[0]
+    return out
+
+
+def build_plans(part, comm, provider, gdim=3, vdeg=1):
+    """Everything dolfinx / PETSc set up behind ``create_matrix`` and ``Mat.assemble`` on more than one rank:
+    the extra pattern entries owners receive for their rows (SparsityPattern.finalize), the column ghosts
+    those entries introduce, the vector halo lists and the ghost-row value-exchange lists.
+
+    ``provider`` builds patterns and returns rows of them: the GPU assembler in production, an oracle-backed
+    stand-in in the CPU tests.  All index exchange goes through ``comm.exchange`` (sparse all-to-all)."""
+    rank = comm.rank
+    n_owned, n_ghost = part.n_owned, part.n_ghost
+    n_dofs = n_owned + n_ghost
+    l2g = np.asarray(part.local_to_global, dtype=np.int64)
+    off = part.global_offset
+    leader, slot, size = entity_tables(part.dofmap, gdim, vdeg, n_dofs)
+    owner_local = np.concatenate([np.full(n_owned, rank, dtype=np.int64), np.asarray(part.ghost_owner, dtype=np.int64)])
+
+    # 1. preliminary pattern from the owned cells; ship the ghost rows' entries to the row owners
+    provider.build_pattern()
+    grow_local = np.arange(n_owned, n_dofs, dtype=np.int32)
+    _, gptr, gidx = provider.get_rows(grow_local)
+    counts = np.diff(gptr)
+    ent_row = np.repeat(grow_local.astype(np.int64), counts)
+    ent_col = gidx.astype(np.int64)
+    row_owner = owner_local[ent_row]
+    send = {}
+    order_by_owner = _group(row_owner)
+    for o, sel in order_by_owner.items():
+        c = ent_col[sel]
+        send[o] = np.stack([l2g[ent_row[sel]], l2g[c], owner_local[c], l2g[leader[c]], slot[c], size[c]], 1).ravel()
+    recv = comm.exchange(send)
+
+    # 2. owners: map received entries to local (row, col); unknown columns become new column ghosts
+    srcs = sorted(recv)
+    msgs = [recv[r].reshape(-1, 6) for r in srcs]
+    lens = [len(m) for m in msgs]
+    m = np.concatenate(msgs) if msgs else np.zeros((0, 6), dtype=np.int64)
+    lrow = m[:, 0] - off
+    assert ((lrow >= 0) & (lrow < n_owned)).all(), "received a row this rank does not own"
+    gcol = m[:, 1]
+    lcol = np.empty(len(gcol), dtype=np.int64)
+    mine = (gcol >= off) & (gcol < off + n_owned)
+    lcol[mine] = gcol[mine] - off
+    gg = np.asarray(part.ghost_global, dtype=np.int64)
+    gorder = np.argsort(gg, kind="stable")
+    gsorted = gg[gorder]
+    nm = np.nonzero(~mine)[0]
+    ug, first, inv = np.unique(gcol[nm], return_index=True, return_inverse=True)
+    pos = np.searchsorted(gsorted, ug)
+    known = (pos < len(gsorted)) & (gsorted[np.minimum(pos, max(len(gsorted) - 1, 0))] == ug) if len(gsorted) else np.zeros(len(ug), bool)
+    ul = np.empty(len(ug), dtype=np.int64)
+    ul[known] = n_owned + gorder[pos[known]]
+    nx = int((~known).sum())
+    ul[~known] = n_dofs + np.arange(nx)
+    lcol[nm] = ul[inv]
+    meta = m[nm[first[~known]]]                                  # first occurrence describes the new column ghost
+    new_global = ug[~known]
+    new_owner, new_gleader, new_slot, new_size = meta[:, 2], meta[:, 3], meta[:, 4], meta[:, 5]
+    lead_pos = np.searchsorted(new_global, new_gleader)
+    assert nx == 0 or (new_global[np.minimum(lead_pos, nx - 1)] == new_gleader).all(), "entity of a new column ghost arrived incomplete"
+    colx_leader = (n_dofs + lead_pos).astype(np.int32)
+    recv_entries, o0 = {}, 0
+    for r, n in zip(srcs, lens):
+        recv_entries[r] = (lrow[o0:o0 + n], lcol[o0:o0 + n])
+        o0 += n
+    extra = (lrow.astype(np.int32), lcol.astype(np.int32), colx_leader, new_slot.astype(np.int32), new_size.astype(np.int32))
+
+    # 3. final pattern
+    provider.build_pattern(*extra)
+    n_cols = n_dofs + nx
+
+    # 4. vector halo over dofmap ghosts + column ghosts
+    ghost_global = np.concatenate([gg, new_global])
+    ghost_owner = np.concatenate([np.asarray(part.ghost_owner, dtype=np.int64), new_owner])
+    req_groups = _group(ghost_owner) if len(ghost_owner) else {}
+    requests = {o: ghost_global[sel] for o, sel in req_groups.items()}
+    asked = comm.exchange(requests)                       # what other ranks need from me
+    neigh = sorted(set(req_groups) | set(asked))
+    send_ptr, send_idx, recv_ptr, recv_idx = [0], [], [0], []
+    for o in neigh:
+        si = (asked[o] - off) if o in asked else np.zeros(0, np.int64)
+        assert ((si >= 0) & (si < n_owned)).all(), "asked for a dof this rank does not own"
+        ri = (n_owned + req_groups[o]) if o in req_groups else np.zeros(0, np.int64)
+        send_idx.append(si); recv_idx.append(ri)
+        send_ptr.append(send_ptr[-1] + len(si)); recv_ptr.append(recv_ptr[-1] + len(ri))
+    cat = lambda a, dt: (np.concatenate(a).astype(dt) if a else np.zeros(0, dt))
+    halo = (np.array(neigh, dtype=np.int32), np.array(send_ptr, dtype=np.int64), cat(send_idx, np.int32),
+            np.array(recv_ptr, dtype=np.int64), cat(recv_idx, np.int32))
+
+    # 5. ghost-row value exchange: senders' positions (final pattern, same entry order as step 1) and
+    #    receivers' positions of the matching (row, col)
+    gstart, gptr2, gidx2 = provider.get_rows(grow_local)
+    assert np.array_equal(gptr2, gptr) and np.array_equal(gidx2, gidx), "ghost rows changed between the two pattern builds"
+    ent_pos = np.repeat(gstart, counts) + (np.arange(len(ent_row)) - np.repeat(gptr[:-1], counts))
+    rneigh = sorted(set(order_by_owner) | set(recv_entries))
+    sp_ptr, sp_pos, rp_ptr, rp_pos = [0], [], [0], []
+    for o in rneigh:
+        spos = ent_pos[order_by_owner[o]] if o in order_by_owner else np.zeros(0, np.int64)
+        if o in recv_entries:
+            lrow, lcol = recv_entries[o]
+            urows, inv = np.unique(lrow, return_inverse=True)
+            ustart, uptr, uidx = provider.get_rows(urows.astype(np.int32))
+            # vectorised search: rows are sorted by column, so (row-rank, column) keys are globally sorted
+            ncol_key = int(max(int(uidx.max()) if len(uidx) else 0, int(lcol.max()) if len(lcol) else 0)) + 1
+            row_of = np.repeat(np.arange(len(urows), dtype=np.int64), np.diff(uptr))
+            keys = row_of * ncol_key + uidx.astype(np.int64)
+            want = inv.astype(np.int64) * ncol_key + lcol
+            j = np.searchsorted(keys, want)
+            assert (j < len(keys)).all() and (keys[np.minimum(j, len(keys) - 1)] == want).all(), "received entry missing from the final pattern"
+            rpos = ustart[inv] + (j - uptr[inv])
+        else:
+            rpos = np.zeros(0, np.int64)
+        sp_pos.append(spos); rp_pos.append(rpos)
+        sp_ptr.append(sp_ptr[-1] + len(spos)); rp_ptr.append(rp_ptr[-1] + len(rpos))
+    rows = (np.array(rneigh, dtype=np.int32), np.array(sp_ptr, dtype=np.int64), cat(sp_pos, np.int64),
+            np.array(rp_ptr, dtype=np.int64), cat(rp_pos, np.int64))
+    return Plans(n_cols, new_global, new_owner, halo, rows, extra)
+
+
 def attach(asm, part, comm):
-    """Create the library's NCCL communicator and install the vector-halo plan."""
+    """Create the library's NCCL communicator (unique id broadcast over the host communicator)."""
     if comm.size == 1:
         return
-    raise NotImplementedError("multi-GPU plans are installed by a later milestone of this round")
+    uid = asm.comm_unique_id() if comm.rank == 0 else None
+    uid = comm.bcast_bytes(uid, 128, root=0)
+    asm.comm_init(comm.rank, comm.size, uid)
 
 
 def finish_pattern_exchange(asm, part, comm):
+    """Build the final pattern and install the halo / ghost-row plans on the assembler."""
     if comm.size == 1:
-        return
-    raise NotImplementedError
+        asm.create_matrix(fetch=False)
+        return None
+    plans = build_plans(part, comm, asm, gdim=asm.gdim, vdeg=asm.vdeg)
+    asm.set_halo(*plans.halo)
+    asm.set_row_exchange(*plans.rows)
+    return plans

@@ -1,0 +1,71 @@
+"""Launched by torchrun (one rank per GPU): distributed GPU assembly / residual / MatMult on the slab-partitioned
+duct against the serial CPU oracle.  Exit code 0 = parity within 1e-12 (relative to the largest entry)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from oracle import oracle
+    from stabilized_navier_stokes_flow_fenicsx_b200 import distributed as D
+    from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+    from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler
+    n_cross, n_long = 6, 20
+    comm = D.Comm.from_env()
+    rank, size = comm.rank, comm.size
+    part = D.duct_partition(n_cross, n_long, rank, size)
+    for kernel in (0, 1):
+        asm = NSAssembler(part.x, part.cells, part.dofmap, vdeg=1, n_dofs_owned=part.n_owned, n_dofs_ghost=part.n_ghost,
+                          n_cells_owned=part.n_cells_owned, device=int(os.environ.get("LOCAL_RANK", 0)))
+        asm.set_form(flavour=0, nu=0.1)
+        asm.set_bcs(part.bcs)
+        asm.set_option("kernel", kernel)
+        D.attach(asm, part, comm)
+        plans = D.finish_pattern_exchange(asm, part, comm)
+        n_owned, n_dofs = part.n_owned, part.n_owned + part.n_ghost
+        # serial oracle
+        m = M.duct_mesh(n_cross, n_long); sp = M.mixed_space(m, 1)
+        w, bcs = M.duct_state(sp), M.duct_bcs(sp)
+        marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs], [b[1] for b in bcs])
+        gp, gi = oracle.build_pattern(sp.dofmap, sp.n_dofs)
+        form = oracle.Form(0, 3, 1, 0.1)
+        gv = oracle.assemble_jacobian(form, m.x, m.cells, sp.dofmap, w, gp, gi, marker, mult)
+        gF = oracle.assemble_residual(form, m.x, m.cells, sp.dofmap, w, marker, value)
+        oracle.set_bc(gF, [b[0] for b in bcs], [b[1] for b in bcs], w)
+        import scipy.sparse as sps
+        A = sps.csr_matrix((gv, gi, gp), shape=(sp.n_dofs,) * 2)
+        l2g = part.local_to_global
+        colg = np.concatenate([l2g, plans.col_ghost_global]) if plans is not None else l2g
+        # ghosts deliberately wrong on input: the forward halo must refresh them
+        xin = part.w.copy()
+        xin[n_owned:] = 1e30
+        vals, F = asm.jacobian_residual(xin)
+        ip = np.empty(n_dofs + 1, dtype=np.int64); ix = np.empty(asm.nnz, dtype=np.int32)
+        asm._check(asm.lib.nsgpu_get_pattern(asm.ctx, ip.ctypes.data, ix.ctypes.data), "get_pattern")
+        worst = 0.0
+        for r in range(n_owned):
+            seg = slice(ip[r], ip[r + 1])
+            gcols = colg[ix[seg]]
+            ref = A.getrow(int(l2g[r]))
+            order = np.argsort(gcols)
+            assert np.array_equal(gcols[order], ref.indices), f"rank {rank}: pattern of row {r} differs"
+            worst = max(worst, np.abs(vals[seg][order] - ref.data).max())
+        assert worst <= 1e-12 * np.abs(gv).max(), f"rank {rank} kernel {kernel}: J err {worst}"
+        eF = np.abs(F[:n_owned] - gF[l2g[:n_owned]]).max()
+        assert eF <= 1e-12 * np.abs(gF).max(), f"rank {rank} kernel {kernel}: F err {eF}"
+        xv = np.random.default_rng(5).standard_normal(sp.n_dofs)
+        xl = np.zeros(n_dofs); xl[:n_owned] = xv[l2g[:n_owned]]
+        y = asm.mult(xl)
+        ey = np.abs(y - (A @ xv)[l2g[:n_owned]]).max()
+        assert ey <= 1e-12 * np.abs(A @ xv).max(), f"rank {rank} kernel {kernel}: MatMult err {ey}"
+        print(f"rank {rank}/{size} kernel {kernel}: J {worst:.2e} F {eF:.2e} Jx {ey:.2e} (n_owned {n_owned}, ghosts {part.n_ghost}, col ghosts {asm.n_cols - n_dofs})", flush=True)
+        asm.close()
+    comm.close()
+
+
+if __name__ == "__main__":
+    main()

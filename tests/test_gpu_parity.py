@@ -189,3 +189,17 @@ def test_size_independent_properties_at_scale():
     ya, yb, yab = asm.mult(a), asm.mult(b), asm.mult(2 * a - 3 * b)
     assert np.abs(yab - (2 * ya - 3 * yb)).max() <= 1e-12 * np.abs(yab).max()
     asm.close()
+
+
+def test_two_gpu_halo_and_row_exchange():
+    """NCCL path (needs >= 2 GPUs on the box; skipped on the single-GPU tier): tests/multigpu_check.py under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
