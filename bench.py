@@ -165,6 +165,8 @@ def run_ours(args):
     asm.set_bcs(part.bcs)
     if args.kernel is not None:
         asm.set_option("kernel", args.kernel)
+    if args.lanes is not None:
+        asm.set_option("lanes", args.lanes)
     if args.threads is not None:
         asm.set_option("threads", args.threads)
     D.attach(asm, part, comm)                                       # the library's own NCCL communicator
@@ -290,7 +292,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NSGPU_WORKLOAD", "L"), choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=None, help="0 auto, 1 generic, 2 fast")
-    ap.add_argument("--threads", type=int, default=None, help="incidences per CTA of the factorised kernel: 128, 192, 256")
+    ap.add_argument("--threads", type=int, default=None, help="CTA size of the factorised kernel")
+    ap.add_argument("--lanes", type=int, default=None, help="lanes per incidence of the factorised kernel: 1 or 4")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -134,7 +134,8 @@ int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_
 int nsgpu_host_alloc_pinned(int64_t bytes, void** out);
 int nsgpu_host_free_pinned(void* p);
 
-/* Options: "kernel" (NSGPU_KERNEL_*), "threads" (incidences per CTA of the factorised kernel: 128, 192 or 256). */
+/* Options: "kernel" (NSGPU_KERNEL_*); for the factorised kernel "lanes" (1 or 4 lanes per vertex-cell incidence) and
+ * "threads" (CTA size: 64..256 with 1 lane, 256..512 with 4 lanes). */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.

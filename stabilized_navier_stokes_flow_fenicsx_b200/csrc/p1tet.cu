@@ -378,6 +378,176 @@ k_p1tet_tiles(FormParams form, const double* __restrict__ xg, const double* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------ quad-lane kernel
+// Same tile / staging / phase-B machinery; phase A runs FOUR lanes per incidence (p1tet_quad), so a tile of CAPI
+// incidences is a CTA of 4*CAPI threads with ~1/2 the registers per thread.
+template <int CAPI, int MINB, bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(4 * CAPI, MINB)
+k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __restrict__ wv, const int32_t* __restrict__ members,
+             const bool contiguous, const uint8_t* __restrict__ bc_marker, const double* __restrict__ bc_value,
+             const uint8_t* __restrict__ cell_bc, const uint32_t* __restrict__ inc_cell, const int4* __restrict__ inc_vtx,
+             const int4* __restrict__ inc_lead, const uint32_t* __restrict__ src, const uint8_t* __restrict__ slot_start,
+             const int2* __restrict__ ent_rel, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
+             const TileHdr* __restrict__ tile_hdr, double* __restrict__ vals, double* __restrict__ F) {
+  constexpr int CAP = CAPI;
+  constexpr int NT = 4 * CAPI;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double4* stageJ = reinterpret_cast<double4*>(smem_raw);
+  double4* stageF = stageJ + (WANT_J ? 16 * CAP : 0);
+  int64_t* s_rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
+  int4* s_rowdof = reinterpret_cast<int4*>(s_rowpos + 4 * CAP);
+  int2* s_rel = reinterpret_cast<int2*>(s_rowdof + CAP);
+  uint32_t* s_src = reinterpret_cast<uint32_t*>(s_rel + (CAP + 2));
+  uint8_t* s_ss = reinterpret_cast<uint8_t*>(s_src + CAP);
+  uint8_t* ent_of_slot = s_ss + (5 * CAP + 16);
+
+  const int tid = threadIdx.x;
+  const TileHdr h = tile_hdr[blockIdx.x];
+  if (h.nent <= 0) return;
+  const int inc = tid >> 2, j = tid & 3;
+  const bool has_inc = inc < h.ninc;
+
+  // ---- tile tables: every thread moves a few entries global -> shared (latency overlaps phase A) ----
+  const int n_ss = h.nslots + h.nent + 1;
+  if (WANT_J) {
+    if (tid < h.ninc) s_src[tid] = src[h.i0 + tid];
+    for (int k = tid; k < n_ss; k += NT) s_ss[k] = slot_start[h.s0 + h.e0 + k];
+  }
+  if (tid < h.nent) {
+    const int2 rel = ent_rel[h.e0 + tid];
+    const int2 reln = (tid + 1 < h.nent) ? ent_rel[h.e0 + tid + 1] : make_int2(h.ninc, h.nslots);
+    s_rel[tid] = rel;
+    s_rowdof[tid] = rowdof[h.e0 + tid];
+    if (WANT_J) {
+      const longlong2* rp = reinterpret_cast<const longlong2*>(rowpos + 4 * (h.e0 + tid));
+      const longlong2 p01 = rp[0], p23 = rp[1];
+      s_rowpos[4 * tid] = p01.x; s_rowpos[4 * tid + 1] = p01.y; s_rowpos[4 * tid + 2] = p23.x; s_rowpos[4 * tid + 3] = p23.y;
+      for (int k = rel.y; k < reln.y; ++k) ent_of_slot[k] = (uint8_t)tid;
+    }
+  }
+  if (tid == 0) s_rel[h.nent] = make_int2(h.ninc, h.nslots);
+
+  // ---------------- phase A: four lanes per incidence ----------------
+  {
+    // lanes of idle quads (inc >= ninc) replay the tile's first incidence so that the quad shuffles stay warp-uniform
+    const int64_t gi = h.i0 + (has_inc ? inc : 0);
+    const int4 vt = inc_vtx[gi];
+    const int4 ld = inc_lead[gi];
+    const uint32_t cm = inc_cell[gi];
+    const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
+    const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
+    double x[4][3], u[4][3], p[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double* xp = xg + 3 * (int64_t)vtx[a];
+      x[a][0] = xp[0]; x[a][1] = xp[1]; x[a][2] = xp[2];
+      if (contiguous) {
+        const double2* wp = reinterpret_cast<const double2*>(wv + lead[a]);
+        const double2 w01 = wp[0], w23 = wp[1];
+        u[a][0] = w01.x; u[a][1] = w01.y; u[a][2] = w23.x; p[a] = w23.y;
+      } else {
+        const int4 mem = reinterpret_cast<const int4*>(members)[lead[a]];
+        u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
+      }
+    }
+    double blk[16], fr[4];
+    const bool row_is_origin = (cm & 3u) == 0;
+    const bool has_bc = cell_bc && cell_bc[cm >> 2];
+    // lifting needs the Jacobian rows even in a residual-only pass; BC cells are rare, so the branch is cheap
+    if (WANT_J) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
+    else if (__any_sync(0xffffffffu, has_bc)) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
+    else p1tet_quad<false, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
+
+    double lift[4] = {0.0, 0.0, 0.0, 0.0};
+    if (has_bc) {
+      // Dirichlet handling at element level (assemble_matrix / apply_lifting semantics)
+      const int lj = (j == 0) ? lead[0] : (j == 1) ? lead[1] : (j == 2) ? lead[2] : lead[3];
+      int cd[4], rd[4];
+      if (contiguous) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { cd[d] = lj + d; rd[d] = lead[0] + d; }
+      } else {
+        const int4 mc = reinterpret_cast<const int4*>(members)[lj];
+        const int4 mr = reinterpret_cast<const int4*>(members)[lead[0]];
+        cd[0] = mc.x; cd[1] = mc.y; cd[2] = mc.z; cd[3] = mc.w;
+        rd[0] = mr.x; rd[1] = mr.y; rd[2] = mr.z; rd[3] = mr.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (bc_marker[cd[d]]) {
+          const double delta = bc_value[cd[d]] - wv[cd[d]];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (WANT_F) lift[r] += blk[4 * r + d] * delta;   // lifting with the un-zeroed entry
+            blk[4 * r + d] = 0.0;                              // constrained trial column
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (bc_marker[rd[r]]) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;    // constrained test row
+        }
+    }
+    if (WANT_F) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) fr[r] += quad_sum(lift[r]);
+    }
+    if (has_inc) {
+      if (WANT_J) {
+        const int sw = inc & 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          stageJ[(j * CAP + inc) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
+      }
+      if (WANT_F && j == 0) stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase B ----------------
+  if (WANT_F) {
+    const int nF = 16 * h.nent;
+    const double* sf = reinterpret_cast<const double*>(stageF);
+    for (int base = 0; base < nF; base += NT) {
+      const int item = base + tid;
+      const int part = item & 3, r = (item >> 2) & 3, le = item >> 4;
+      double acc = 0.0;
+      if (le < h.nent)
+        for (int ii = s_rel[le].x + part; ii < s_rel[le + 1].x; ii += 4) acc += sf[4 * ii + r];
+      acc = quad_sum(acc);
+      if (le < h.nent && part == 0) {
+        const int4 rd = s_rowdof[le];
+        F[(r == 0) ? rd.x : (r == 1) ? rd.y : (r == 2) ? rd.z : rd.w] = acc;
+      }
+    }
+  }
+  if (WANT_J) {
+    const int nitems = 4 * h.nslots;
+    const uint8_t* srcb = reinterpret_cast<const uint8_t*>(s_src);
+    for (int item = tid; item < nitems; item += NT) {
+      const int ls = item >> 2, r = item & 3;
+      const int le = ent_of_slot[ls];
+      const int2 rel = s_rel[le];
+      const int s = ls - rel.y;
+      const uint8_t* ss = s_ss + ls + le;
+      const int jb = ss[0], je = ss[1];
+      const uint8_t* sp = srcb + 4 * rel.x;
+      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+      for (int q = jb; q < je; ++q) {
+        const int code = sp[q];
+        const int ii = rel.x + (code >> 2), a = code & 3;
+        const double4 v = stageJ[(a * CAP + ii) * 4 + (r ^ (ii & 3))];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      double* dst = vals + s_rowpos[4 * le + r] + 4 * s;
+      __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
+      __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
@@ -393,10 +563,14 @@ void p1tet_mark_bc_dirty(nsgpu_ctx* ctx) {
   if (ctx->p1plan) ctx->p1plan->bc_dirty = true;
 }
 
-static int plan_cap(nsgpu_ctx* ctx) { return ctx->threads == 256 ? 256 : (ctx->threads == 192 ? 192 : 128); }
+static bool use_quad(nsgpu_ctx* ctx) { return ctx->lanes == 4; }
+static int plan_cap(nsgpu_ctx* ctx) { return use_quad(ctx) ? ctx->threads / 4 : ctx->threads; }   // incidences per tile
 // launch-bounds pairing: 256 -> 1 CTA/SM, 192 -> 1, 128 -> 2 (all at the full 255-register budget)
 
 bool p1tet_fast_available(nsgpu_ctx* ctx) {
+  // valid (lanes, threads) pairs: 1 x {64,128,192,256}; 4 x {256,384,512}
+  if (ctx->lanes == 4 && ctx->threads < 256) ctx->threads = 256;
+  if (ctx->lanes == 1 && ctx->threads > 256) ctx->threads = 256;
   if (ctx->gdim != 3 || ctx->vdeg != 1 || !ctx->pattern_built || !ctx->rows_presorted || !ctx->d_pairs) return false;
   if (ctx->n_cells_owned >= ((int64_t)1 << 29)) return false;
   if (ctx->p1plan && ctx->p1plan->cap != plan_cap(ctx)) p1tet_free(ctx);
@@ -414,6 +588,14 @@ static cudaError_t set_smem_attr() {
   if ((e = cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(true)))) return e;
   if ((e = cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(true)))) return e;
   return cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(false));
+}
+
+template <int CAPI, int MINB>
+static cudaError_t set_smem_attr_quad() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(true)))) return e;
+  if ((e = cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(true)))) return e;
+  return cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(false));
 }
 
 int p1tet_build_plan(nsgpu_ctx* ctx) {
@@ -566,7 +748,9 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->contiguous = flags[1] == 0;
   P->bc_dirty = true;
   ctx->p1plan = P;
-  cudaError_t e = CAPV == 256 ? set_smem_attr<256, 1>() : (CAPV == 192 ? set_smem_attr<192, 1>() : set_smem_attr<128, 2>());
+  cudaError_t e = cudaSuccess;
+  if (use_quad(ctx)) e = CAPV == 128 ? set_smem_attr_quad<128, 1>() : (CAPV == 96 ? set_smem_attr_quad<96, 1>() : set_smem_attr_quad<64, 2>());
+  else e = CAPV == 256 ? set_smem_attr<256, 1>() : (CAPV == 192 ? set_smem_attr<192, 1>() : (CAPV == 128 ? set_smem_attr<128, 2>() : set_smem_attr<64, 4>()));
   if (e != cudaSuccess) { set_error(ctx, std::string("p1tet plan: smem attribute: ") + cudaGetErrorString(e)); p1tet_free(ctx); return NSGPU_ECUDA; }
   return NSGPU_OK;
 #undef PL_CUDA
@@ -586,6 +770,20 @@ static void launch_tiles(nsgpu_ctx* ctx, nsgpu_p1tet_plan* P, const double* d_xi
 #undef P1_LAUNCH
 }
 
+template <int CAPI, int MINB>
+static void launch_quad(nsgpu_ctx* ctx, nsgpu_p1tet_plan* P, const double* d_xin, bool want_J, bool want_F, double* d_Fout, const uint8_t* cbc) {
+  cudaStream_t s = ctx->stream;
+#define P1Q_LAUNCH(J, F)                                                                                             \
+  k_p1tet_quad<CAPI, MINB, J, F><<<(unsigned)P->n_tiles, 4 * CAPI, TileSmem<CAPI>::bytes(J), s>>>(ctx->form, ctx->d_x, d_xin,   \
+      ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead,  \
+      reinterpret_cast<const uint32_t*>(P->d_src), P->d_slot_start, P->d_ent_rel, P->d_rowpos,                            \
+      reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout)
+  if (want_J && want_F) P1Q_LAUNCH(true, true);
+  else if (want_J) P1Q_LAUNCH(true, false);
+  else P1Q_LAUNCH(false, true);
+#undef P1Q_LAUNCH
+}
+
 int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) { set_error(ctx, "p1tet plan missing"); return NSGPU_EINVAL; }
@@ -597,9 +795,14 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
     ctx->launches += 1;
   }
   const uint8_t* cbc = ctx->has_bc ? P->d_cell_bc : nullptr;
-  if (P->cap == 256) launch_tiles<256, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+  if (use_quad(ctx)) {
+    if (P->cap == 128) launch_quad<128, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+    else if (P->cap == 96) launch_quad<96, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+    else launch_quad<64, 2>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+  } else if (P->cap == 256) launch_tiles<256, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
   else if (P->cap == 192) launch_tiles<192, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-  else launch_tiles<128, 2>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+  else if (P->cap == 128) launch_tiles<128, 2>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+  else launch_tiles<64, 4>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
   return NSGPU_OK;

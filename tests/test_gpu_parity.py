@@ -86,16 +86,25 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     asm.close()
 
 
-def test_generic_and_fast_kernels_agree(oracle):
+@pytest.mark.parametrize("kernel,lanes,threads", [(1, 1, 128), (2, 1, 64), (2, 1, 128), (2, 1, 192), (2, 1, 256), (2, 4, 256), (2, 4, 384), (2, 4, 512)])
+def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads):
+    """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernel, which must apply;
+    lanes 1: one thread per incidence, lanes 4: four lanes per incidence."""
     m, sp, w, bcs, fk = _case("duct_p1")
+    w = w + 0.01 * np.random.default_rng(4).standard_normal(sp.n_dofs)     # off the Dirichlet values: lifting active
     indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
-    for kernel in (1, 2):   # 1 = generic (thread per cell row, atomics), 2 = factorised row-owner kernel (must apply)
-        asm = _gpu(m, sp, bcs, fk, kernel)
-        asm.create_matrix(fetch=False)
-        gv, gF = asm.jacobian_residual(w)
-        assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
-        assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
-        asm.close()
+    asm = _gpu(m, sp, bcs, fk, kernel)
+    asm.set_option("lanes", lanes)
+    asm.set_option("threads", threads)
+    asm.create_matrix(fetch=False)
+    gv, gF = asm.jacobian_residual(w)
+    assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+    assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    gF2 = asm.residual(w)                                                   # residual-only pass (lifting still needs J rows)
+    assert np.abs(gF2 - F).max() <= RTOL * np.abs(F).max()
+    gv2 = asm.jacobian(w)
+    assert np.abs(gv2 - vals).max() <= RTOL * np.abs(vals).max()
+    asm.close()
 
 
 def test_lifting_with_state_off_the_dirichlet_values(oracle):
