@@ -26,25 +26,26 @@
 #include "element_p1tet.cuh"
 
 struct TileHdr {
-  int64_t e0, i0, s0;
+  int64_t e0;      // first vertex (entity) of the tile
+  int64_t boff;    // offset of the tile's byte tables in d_tile_bytes (16-byte aligned)
   int nent, ninc, nslots, pad;
 };
 
 struct nsgpu_p1tet_plan {
   int64_t n_inc = 0, n_ent = 0, n_tiles = 0, n_slots = 0;
   int cap = 0, maxdeg = 0;
-  uint32_t* d_inc_cell = nullptr;   // [n_inc] cell * 4 + local vertex, sorted by row vertex
-  int4* d_inc_vtx = nullptr;        // [n_inc] geometry vertex ids, row vertex first (rotated order)
-  int4* d_inc_lead = nullptr;       // [n_inc] first dof of the 4 vertices, same order
-  uint8_t* d_src = nullptr;         // [4 n_inc] gather lists: (incidence-within-vertex << 2 | block), grouped by slot
-  uint8_t* d_slot_start = nullptr;  // [n_slots + n_ent] per vertex: ns + 1 list offsets inside its 4 * deg items
-  int64_t* d_inc_ptr = nullptr;     // [n_ent + 1]
-  int64_t* d_slot_ptr = nullptr;    // [n_ent + 1] prefix of neighbour counts
+  // per incidence, TILE-PADDED: entry k of tile t lives at t * cap + k (so phase-A loads do not wait for the header)
+  uint32_t* d_inc_cell = nullptr;   // cell * 4 + local vertex
+  int4* d_inc_vtx = nullptr;        // geometry vertex ids, row vertex first (rotated order)
+  int4* d_inc_lead = nullptr;       // first dof of the 4 vertices, same order
+  uint32_t* d_src = nullptr;        // gather lists, 4 bytes per incidence: (incidence-within-vertex << 2 | block), grouped by slot
+  // per vertex (entity), compact
+  int2* d_ent_rel = nullptr;        // (incidence offset, slot offset) relative to the tile start
   int64_t* d_rowpos = nullptr;      // [n_ent * 4] CSR start of the vertex's 4 rows
   int32_t* d_rowdof = nullptr;      // [n_ent * 4] the vertex's 4 dofs
-  int64_t* d_tile_ent = nullptr;    // [n_tiles + 1]
+  // per tile
   TileHdr* d_tile_hdr = nullptr;    // [n_tiles]
-  int2* d_ent_rel = nullptr;        // [n_ent] (incidence offset, slot offset) relative to the tile start
+  uint8_t* d_tile_bytes = nullptr;  // per tile: slot-list offsets | vertex of each slot | diagonal slot of each vertex (16-B padded segments)
   uint8_t* d_cell_bc = nullptr;     // [n_cells] cell touches a Dirichlet dof
   bool contiguous = false;          // every vertex's dofs are (first dof) + 0,1,2,3 and first dof is even
   bool bc_dirty = true;
@@ -67,12 +68,23 @@ struct HiWord {
 
 __global__ void k_ent_info(int64_t n_ent, const uint32_t* __restrict__ ent_leader, const int32_t* __restrict__ members,
                            const int64_t* __restrict__ pfirst, const int64_t* __restrict__ plast,
-                           const int64_t* __restrict__ indptr, int64_t* nslots, int64_t* rowpos, int32_t* rowdof, int* not_contig) {
+                           const uint64_t* __restrict__ pairs, const int64_t* __restrict__ indptr, int64_t* nslots, int64_t* rowpos,
+                           int32_t* rowdof, uint8_t* diag_slot, int* not_contig) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e > n_ent) return;
   if (e == n_ent) { nslots[e] = 0; return; }
   const uint32_t A = ent_leader[e];
   nslots[e] = plast[A] - pfirst[A];
+  {  // slot of the vertex in its own neighbour list (the diagonal block)
+    int64_t lo = pfirst[A], hi = plast[A] - 1, found = 0;
+    while (lo <= hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const uint32_t v = (uint32_t)(pairs[mid] & 0xffffffffu);
+      if (v == A) { found = mid - pfirst[A]; break; }
+      if (v < A) lo = mid + 1; else hi = mid - 1;
+    }
+    diag_slot[e] = (uint8_t)found;
+  }
   bool ok = (A & 1u) == 0;
   for (int c = 0; c < 4; ++c) {
     const int32_t d = members[(int64_t)A * KMAX + c];
@@ -157,24 +169,49 @@ __global__ void k_tiles(int64_t n_tiles, int64_t n_ent, int64_t capeff, const in
   tile_ent[t] = lo;
 }
 
-__global__ void k_tile_hdr(int64_t n_tiles, const int64_t* __restrict__ tile_ent, const int64_t* __restrict__ inc_ptr,
-                           const int64_t* __restrict__ slot_ptr, TileHdr* hdr) {
+__host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
+
+__global__ void k_tile_sizes(int64_t n_tiles, const int64_t* __restrict__ tile_ent, const int64_t* __restrict__ slot_ptr, int64_t* sizes) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  TileHdr h;
-  h.e0 = tile_ent[t];
-  const int64_t e1 = tile_ent[t + 1];
-  h.i0 = inc_ptr[h.e0]; h.s0 = slot_ptr[h.e0];
-  h.nent = (int)(e1 - h.e0); h.ninc = (int)(inc_ptr[e1] - h.i0); h.nslots = (int)(slot_ptr[e1] - h.s0); h.pad = 0;
-  hdr[t] = h;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { sizes[t] = 0; return; }
+  const int64_t e0 = tile_ent[t], e1 = tile_ent[t + 1];
+  const int nent = (int)(e1 - e0), nslots = (int)(slot_ptr[e1] - slot_ptr[e0]);
+  sizes[t] = pad16(nslots + nent + 1) + pad16(nslots) + pad16(nent);
 }
 
-__global__ void k_ent_rel(int64_t n_tiles, const TileHdr* __restrict__ hdr, const int64_t* __restrict__ inc_ptr,
-                          const int64_t* __restrict__ slot_ptr, int2* ent_rel) {
+// one CTA per tile: header, tile-relative vertex offsets, tile-padded incidence arrays, byte tables
+__global__ void k_tile_pack(int cap, const int64_t* __restrict__ tile_ent, const int64_t* __restrict__ inc_ptr,
+                            const int64_t* __restrict__ slot_ptr, const int64_t* __restrict__ boff, const uint32_t* __restrict__ c_cell,
+                            const int4* __restrict__ c_vtx, const int4* __restrict__ c_lead, const uint32_t* __restrict__ c_src,
+                            const uint8_t* __restrict__ slot_start, const uint8_t* __restrict__ diag_slot, TileHdr* hdr, int2* ent_rel,
+                            uint32_t* p_cell, int4* p_vtx, int4* p_lead, uint32_t* p_src, uint8_t* bytes) {
   const int64_t t = blockIdx.x;
-  const TileHdr h = hdr[t];
-  for (int k = threadIdx.x; k < h.nent; k += blockDim.x)
-    ent_rel[h.e0 + k] = make_int2((int)(inc_ptr[h.e0 + k] - h.i0), (int)(slot_ptr[h.e0 + k] - h.s0));
+  const int64_t e0 = tile_ent[t], e1 = tile_ent[t + 1];
+  const int64_t i0 = inc_ptr[e0], s0 = slot_ptr[e0];
+  const int nent = (int)(e1 - e0), ninc = (int)(inc_ptr[e1] - i0), nslots = (int)(slot_ptr[e1] - s0);
+  if (threadIdx.x == 0) {
+    TileHdr h;
+    h.e0 = e0; h.boff = boff[t]; h.nent = nent; h.ninc = ninc; h.nslots = nslots; h.pad = 0;
+    hdr[t] = h;
+  }
+  for (int k = threadIdx.x; k < cap; k += blockDim.x) {
+    const bool in = k < ninc;
+    p_cell[t * cap + k] = in ? c_cell[i0 + k] : 0u;
+    p_vtx[t * cap + k] = in ? c_vtx[i0 + k] : make_int4(0, 0, 0, 0);
+    p_lead[t * cap + k] = in ? c_lead[i0 + k] : make_int4(0, 0, 0, 0);
+    p_src[t * cap + k] = in ? c_src[i0 + k] : 0u;
+  }
+  uint8_t* b = bytes + boff[t];
+  const int n_ss = nslots + nent + 1;
+  uint8_t* eos = b + pad16(n_ss);
+  uint8_t* dg = eos + pad16(nslots);
+  for (int k = threadIdx.x; k < n_ss; k += blockDim.x) b[k] = slot_start[s0 + e0 + k];
+  for (int k = threadIdx.x; k < nent; k += blockDim.x) {
+    ent_rel[e0 + k] = make_int2((int)(inc_ptr[e0 + k] - i0), (int)(slot_ptr[e0 + k] - s0));
+    dg[k] = diag_slot[e0 + k];
+    for (int64_t g = slot_ptr[e0 + k]; g < slot_ptr[e0 + k + 1]; ++g) eos[g - s0] = (uint8_t)k;
+  }
 }
 
 __global__ void k_cell_bc(int64_t n_cells, const int32_t* __restrict__ dofmap, const uint8_t* __restrict__ marker, uint8_t* cell_bc) {
@@ -185,69 +222,158 @@ __global__ void k_cell_bc(int64_t n_cells, const int32_t* __restrict__ dofmap, c
   cell_bc[c] = f;
 }
 
-// ------------------------------------------------------------------------------------------ the kernel
+// ------------------------------------------------------------------------------------------ the kernels
 template <int CAP> struct TileSmem {
   // stageJ [4 blocks][CAP][4 rows] double4 (row index swizzled by incidence) | stageF [CAP] double4 |
-  // rowpos [CAP][4] i64 | rowdof [CAP][4] i32 | rel [CAP+1] int2 | src [CAP] u32 | slot_start [5 CAP + 8] u8 |
-  // ent_of_slot [4 CAP] u8
+  // rowpos [CAP][4] i64 | rowdof [CAP] int4 | rel [CAP+2] int2 | src [CAP] u32 | byte tables
+  static constexpr int kBytes = ((5 * CAP + 1 + 15) & ~15) + ((4 * CAP + 15) & ~15) + ((CAP + 15) & ~15);
   static constexpr size_t stageJ = 16 * (size_t)CAP * sizeof(double4);
   static constexpr size_t stageF = (size_t)CAP * sizeof(double4);
-  static constexpr size_t tables = 32 * CAP + 16 * CAP + 8 * (CAP + 2) + 4 * CAP + (5 * CAP + 16) + 4 * CAP;
+  static constexpr size_t tables = 32 * CAP + 16 * CAP + 8 * (CAP + 2) + 4 * CAP + kBytes;
   static constexpr size_t bytes(bool want_J) { return (want_J ? stageJ : 0) + stageF + tables; }
 };
 
-template <int CAP, int MINB, bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(CAP, MINB)
-k_p1tet_tiles(FormParams form, const double* __restrict__ xg, const double* __restrict__ wv, const int32_t* __restrict__ members,
-              const bool contiguous, const uint8_t* __restrict__ bc_marker, const double* __restrict__ bc_value,
-              const uint8_t* __restrict__ cell_bc, const uint32_t* __restrict__ inc_cell, const int4* __restrict__ inc_vtx,
-              const int4* __restrict__ inc_lead, const uint32_t* __restrict__ src, const uint8_t* __restrict__ slot_start,
-              const int2* __restrict__ ent_rel, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
-              const TileHdr* __restrict__ tile_hdr, double* __restrict__ vals, double* __restrict__ F) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double4* stageJ = reinterpret_cast<double4*>(smem_raw);
-  double4* stageF = stageJ + (WANT_J ? 16 * CAP : 0);
-  int64_t* s_rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
-  int4* s_rowdof = reinterpret_cast<int4*>(s_rowpos + 4 * CAP);
-  int2* s_rel = reinterpret_cast<int2*>(s_rowdof + CAP);
-  uint32_t* s_src = reinterpret_cast<uint32_t*>(s_rel + (CAP + 2));
-  uint8_t* s_ss = reinterpret_cast<uint8_t*>(s_src + CAP);
-  uint8_t* ent_of_slot = s_ss + (5 * CAP + 16);
-
-  const int tid = threadIdx.x;
-  const TileHdr h = tile_hdr[blockIdx.x];
-  if (h.nent <= 0) return;
-
-  // ---- issue every table load of the tile up front: their latency hides behind phase A ----
-  const bool has_inc = tid < h.ninc, has_ent = tid < h.nent;
-  uint32_t r_src = 0;
-  int2 r_rel = make_int2(h.ninc, h.nslots), r_rel_next = make_int2(h.ninc, h.nslots);
-  int64_t r_rowpos[4] = {0, 0, 0, 0};
-  int4 r_rowdof = make_int4(0, 0, 0, 0);
-  uint8_t r_ss[5] = {0, 0, 0, 0, 0};
-  const int n_ss = h.nslots + h.nent + 1;
-  if (WANT_J) {
-    if (has_inc) r_src = src[h.i0 + tid];
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (tid + k * CAP < n_ss) r_ss[k] = slot_start[h.s0 + h.e0 + tid + k * CAP];
+template <int CAP, bool WANT_J> struct TileView {
+  double4* stageJ; double4* stageF; int64_t* rowpos; int4* rowdof; int2* rel; uint32_t* src; uint8_t* bytes;
+  __device__ explicit TileView(unsigned char* raw) {
+    stageJ = reinterpret_cast<double4*>(raw);
+    stageF = stageJ + (WANT_J ? 16 * CAP : 0);
+    rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
+    rowdof = reinterpret_cast<int4*>(rowpos + 4 * CAP);
+    rel = reinterpret_cast<int2*>(rowdof + CAP);
+    src = reinterpret_cast<uint32_t*>(rel + (CAP + 2));
+    bytes = reinterpret_cast<uint8_t*>(src + CAP);
   }
-  if (has_ent) {
-    r_rel = ent_rel[h.e0 + tid];
-    if (tid + 1 < h.nent) r_rel_next = ent_rel[h.e0 + tid + 1];
-    r_rowdof = rowdof[h.e0 + tid];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// asynchronous global -> shared copy of the tile's tables (no registers held; completes behind phase A)
+template <int CAP, int NT, bool WANT_J>
+__device__ __forceinline__ void tile_tables_async(const TileView<CAP, WANT_J>& v, const TileHdr& h, int tid, int64_t tile,
+                                                  const uint32_t* __restrict__ src, const uint8_t* __restrict__ tile_bytes,
+                                                  const int2* __restrict__ ent_rel, const int64_t* __restrict__ rowpos,
+                                                  const int4* __restrict__ rowdof) {
+  if (WANT_J) {
+    for (int k = tid; k < CAP / 4; k += NT) cp_async16(v.src + 4 * k, src + tile * CAP + 4 * k);
+    const int nb = (pad16(h.nslots + h.nent + 1) + pad16(h.nslots) + pad16(h.nent)) >> 4;
+    for (int k = tid; k < nb; k += NT) cp_async16(v.bytes + 16 * k, tile_bytes + h.boff + 16 * k);
+  }
+  for (int k = tid; k < h.nent; k += NT) {
+    cp_async8(v.rel + k, ent_rel + h.e0 + k);
+    cp_async16(v.rowdof + k, rowdof + h.e0 + k);
     if (WANT_J) {
-      const longlong2* rp = reinterpret_cast<const longlong2*>(rowpos + 4 * (h.e0 + tid));
-      const longlong2 p01 = rp[0], p23 = rp[1];
-      r_rowpos[0] = p01.x; r_rowpos[1] = p01.y; r_rowpos[2] = p23.x; r_rowpos[3] = p23.y;
+      cp_async16(v.rowpos + 4 * k, rowpos + 4 * (h.e0 + k));
+      cp_async16(v.rowpos + 4 * k + 2, rowpos + 4 * (h.e0 + k) + 2);
     }
   }
+  if (tid == 0) v.rel[h.nent] = make_int2(h.ninc, h.nslots);
+}
 
-  // ---------------- phase A: one incidence per thread ----------------
-  if (has_inc) {
-    const int4 vt = inc_vtx[h.i0 + tid];
-    const int4 ld = inc_lead[h.i0 + tid];
-    const uint32_t cm = inc_cell[h.i0 + tid];
+__device__ __forceinline__ double quad_sum_b(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// phase B: gather the parked row slabs into finished CSR row pieces (and residual entries)
+template <int CAP, int NT, bool WANT_J, bool WANT_F>
+__device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, const TileHdr& h, int tid, double* __restrict__ vals,
+                                            double* __restrict__ F) {
+  const uint8_t* s_ss = v.bytes;
+  const uint8_t* eos = v.bytes + pad16(h.nslots + h.nent + 1);
+  const uint8_t* dg = eos + pad16(h.nslots);
+  if (WANT_J) {
+    // off-diagonal slots: one (slot, row) piece per thread, 4-6 parked blocks each
+    const int nitems = 4 * h.nslots;
+    const uint8_t* srcb = reinterpret_cast<const uint8_t*>(v.src);
+    for (int item = tid; item < nitems; item += NT) {
+      const int ls = item >> 2, r = item & 3;
+      const int le = eos[ls];
+      const int2 rel = v.rel[le];
+      const int s = ls - rel.y;
+      if (s == dg[le]) continue;                       // the diagonal block is gathered below, four lanes per piece
+      const uint8_t* ss = s_ss + ls + le;
+      const int jb = ss[0], je = ss[1];
+      const uint8_t* sp = srcb + 4 * rel.x;
+      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+      for (int q = jb; q < je; ++q) {
+        const int code = sp[q];
+        const int ii = rel.x + (code >> 2), a = code & 3;
+        const double4 w = v.stageJ[(a * CAP + ii) * 4 + (r ^ (ii & 3))];
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+      }
+      double* dst = vals + v.rowpos[4 * le + r] + 4 * s;
+      __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
+      __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
+    }
+  }
+  {
+    // diagonal block (block 0 of every incidence of the vertex) and residual: (vertex, row) sums, four lanes each
+    const int nD = 16 * h.nent;
+    const double* sf = reinterpret_cast<const double*>(v.stageF);
+    for (int base = 0; base < nD; base += NT) {
+      const int item = base + tid;
+      const int part = item & 3, r = (item >> 2) & 3, le = item >> 4;
+      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+      double accF = 0.0;
+      if (le < h.nent) {
+        const int ib = v.rel[le].x, ie = v.rel[le + 1].x;
+        for (int ii = ib + part; ii < ie; ii += 4) {
+          if (WANT_J) {
+            const double4 w = v.stageJ[ii * 4 + (r ^ (ii & 3))];
+            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+          }
+          if (WANT_F) accF += sf[4 * ii + r];
+        }
+      }
+      if (WANT_J) { acc.x = quad_sum_b(acc.x); acc.y = quad_sum_b(acc.y); acc.z = quad_sum_b(acc.z); acc.w = quad_sum_b(acc.w); }
+      if (WANT_F) accF = quad_sum_b(accF);
+      if (le < h.nent && part == 0) {
+        if (WANT_J) {
+          double* dst = vals + v.rowpos[4 * le + r] + 4 * dg[le];
+          __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
+          __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
+        }
+        if (WANT_F) {
+          const int4 rd = v.rowdof[le];
+          F[(r == 0) ? rd.x : (r == 1) ? rd.y : (r == 2) ? rd.z : rd.w] = accF;
+        }
+      }
+    }
+  }
+}
+
+#define P1_KERNEL_ARGS                                                                                                     \
+  FormParams form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,          \
+      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value,                        \
+      const uint8_t *__restrict__ cell_bc, const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,              \
+      const int4 *__restrict__ inc_lead, const uint32_t *__restrict__ src, const uint8_t *__restrict__ tile_bytes,               \
+      const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
+      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F
+
+// one thread per incidence
+template <int CAP, int MINB, bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TileView<CAP, WANT_J> v(smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  // phase-A inputs are tile-padded: their loads do not depend on the header
+  const int4 vt = inc_vtx[tile * CAP + tid];
+  const int4 ld = inc_lead[tile * CAP + tid];
+  const uint32_t cm = inc_cell[tile * CAP + tid];
+  const TileHdr h = tile_hdr[tile];
+  if (h.nent <= 0) return;
+  tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+
+  if (tid < h.ninc) {
     const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
     const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
     double x[4][3], u[4][3], p[4];
@@ -310,130 +436,33 @@ k_p1tet_tiles(FormParams form, const double* __restrict__ xg, const double* __re
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          stageJ[(a * CAP + tid) * 4 + (r ^ sw)] = make_double4(blk[a][4 * r], blk[a][4 * r + 1], blk[a][4 * r + 2], blk[a][4 * r + 3]);
+          v.stageJ[(a * CAP + tid) * 4 + (r ^ sw)] = make_double4(blk[a][4 * r], blk[a][4 * r + 1], blk[a][4 * r + 2], blk[a][4 * r + 3]);
     }
-    if (WANT_F) stageF[tid] = make_double4(fr[0], fr[1], fr[2], fr[3]);
+    if (WANT_F) v.stageF[tid] = make_double4(fr[0], fr[1], fr[2], fr[3]);
   }
-  // park the tables
-  if (WANT_J) {
-    if (has_inc) s_src[tid] = r_src;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (tid + k * CAP < n_ss) s_ss[tid + k * CAP] = r_ss[k];
-  }
-  if (has_ent) {
-    s_rel[tid] = r_rel;
-    s_rowdof[tid] = r_rowdof;
-    if (WANT_J) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) s_rowpos[4 * tid + r] = r_rowpos[r];
-      for (int k = r_rel.y; k < r_rel_next.y; ++k) ent_of_slot[k] = (uint8_t)tid;
-    }
-  }
-  if (tid == 0) s_rel[h.nent] = make_int2(h.ninc, h.nslots);
+  cp_async_wait_all();
   __syncthreads();
-
-  // ---------------- phase B ----------------
-  if (WANT_F) {
-    // residual: (vertex, row) sums over the vertex's incidences, four lanes per sum
-    const int nF = 16 * h.nent;
-    const double* sf = reinterpret_cast<const double*>(stageF);
-    for (int base = 0; base < nF; base += CAP) {
-      const int item = base + tid;
-      const int part = item & 3, r = (item >> 2) & 3, le = item >> 4;
-      double acc = 0.0;
-      if (le < h.nent)
-        for (int ii = s_rel[le].x + part; ii < s_rel[le + 1].x; ii += 4) acc += sf[4 * ii + r];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (le < h.nent && part == 0) {
-        const int4 rd = s_rowdof[le];
-        F[(r == 0) ? rd.x : (r == 1) ? rd.y : (r == 2) ? rd.z : rd.w] = acc;
-      }
-    }
-  }
-  if (WANT_J) {
-    // Jacobian: one (vertex, slot, row) piece per thread
-    const int nitems = 4 * h.nslots;
-    const uint8_t* srcb = reinterpret_cast<const uint8_t*>(s_src);
-    for (int item = tid; item < nitems; item += CAP) {
-      const int ls = item >> 2, r = item & 3;
-      const int le = ent_of_slot[ls];
-      const int2 rel = s_rel[le];
-      const int s = ls - rel.y;
-      const uint8_t* ss = s_ss + ls + le;
-      const int jb = ss[0], je = ss[1];
-      const uint8_t* sp = srcb + 4 * rel.x;
-      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
-      for (int j = jb; j < je; ++j) {
-        const int code = sp[j];
-        const int ii = rel.x + (code >> 2), a = code & 3;
-        const double4 v = stageJ[(a * CAP + ii) * 4 + (r ^ (ii & 3))];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      double* dst = vals + s_rowpos[4 * le + r] + 4 * s;
-      __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
-      __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
-    }
-  }
+  tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
 }
 
-// ------------------------------------------------------------------------------------------ quad-lane kernel
-// Same tile / staging / phase-B machinery; phase A runs FOUR lanes per incidence (p1tet_quad), so a tile of CAPI
-// incidences is a CTA of 4*CAPI threads with ~1/2 the registers per thread.
+// four lanes per incidence (p1tet_quad): a tile of CAPI incidences is a CTA of 4 * CAPI threads
 template <int CAPI, int MINB, bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(4 * CAPI, MINB)
-k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __restrict__ wv, const int32_t* __restrict__ members,
-             const bool contiguous, const uint8_t* __restrict__ bc_marker, const double* __restrict__ bc_value,
-             const uint8_t* __restrict__ cell_bc, const uint32_t* __restrict__ inc_cell, const int4* __restrict__ inc_vtx,
-             const int4* __restrict__ inc_lead, const uint32_t* __restrict__ src, const uint8_t* __restrict__ slot_start,
-             const int2* __restrict__ ent_rel, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
-             const TileHdr* __restrict__ tile_hdr, double* __restrict__ vals, double* __restrict__ F) {
+__global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
   constexpr int CAP = CAPI;
   constexpr int NT = 4 * CAPI;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double4* stageJ = reinterpret_cast<double4*>(smem_raw);
-  double4* stageF = stageJ + (WANT_J ? 16 * CAP : 0);
-  int64_t* s_rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
-  int4* s_rowdof = reinterpret_cast<int4*>(s_rowpos + 4 * CAP);
-  int2* s_rel = reinterpret_cast<int2*>(s_rowdof + CAP);
-  uint32_t* s_src = reinterpret_cast<uint32_t*>(s_rel + (CAP + 2));
-  uint8_t* s_ss = reinterpret_cast<uint8_t*>(s_src + CAP);
-  uint8_t* ent_of_slot = s_ss + (5 * CAP + 16);
-
+  const TileView<CAP, WANT_J> v(smem_raw);
   const int tid = threadIdx.x;
-  const TileHdr h = tile_hdr[blockIdx.x];
-  if (h.nent <= 0) return;
+  const int64_t tile = blockIdx.x;
   const int inc = tid >> 2, j = tid & 3;
-  const bool has_inc = inc < h.ninc;
-
-  // ---- tile tables: every thread moves a few entries global -> shared (latency overlaps phase A) ----
-  const int n_ss = h.nslots + h.nent + 1;
-  if (WANT_J) {
-    if (tid < h.ninc) s_src[tid] = src[h.i0 + tid];
-    for (int k = tid; k < n_ss; k += NT) s_ss[k] = slot_start[h.s0 + h.e0 + k];
-  }
-  if (tid < h.nent) {
-    const int2 rel = ent_rel[h.e0 + tid];
-    const int2 reln = (tid + 1 < h.nent) ? ent_rel[h.e0 + tid + 1] : make_int2(h.ninc, h.nslots);
-    s_rel[tid] = rel;
-    s_rowdof[tid] = rowdof[h.e0 + tid];
-    if (WANT_J) {
-      const longlong2* rp = reinterpret_cast<const longlong2*>(rowpos + 4 * (h.e0 + tid));
-      const longlong2 p01 = rp[0], p23 = rp[1];
-      s_rowpos[4 * tid] = p01.x; s_rowpos[4 * tid + 1] = p01.y; s_rowpos[4 * tid + 2] = p23.x; s_rowpos[4 * tid + 3] = p23.y;
-      for (int k = rel.y; k < reln.y; ++k) ent_of_slot[k] = (uint8_t)tid;
-    }
-  }
-  if (tid == 0) s_rel[h.nent] = make_int2(h.ninc, h.nslots);
-
-  // ---------------- phase A: four lanes per incidence ----------------
+  const int4 vt = inc_vtx[tile * CAP + inc];
+  const int4 ld = inc_lead[tile * CAP + inc];
+  const uint32_t cm = inc_cell[tile * CAP + inc];
+  const TileHdr h = tile_hdr[tile];
+  if (h.nent <= 0) return;
+  tile_tables_async<CAP, NT, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+  const bool has_inc = inc < h.ninc;   // padded entries point at vertex 0 / dof 0: harmless loads, results discarded
   {
-    // lanes of idle quads (inc >= ninc) replay the tile's first incidence so that the quad shuffles stay warp-uniform
-    const int64_t gi = h.i0 + (has_inc ? inc : 0);
-    const int4 vt = inc_vtx[gi];
-    const int4 ld = inc_lead[gi];
-    const uint32_t cm = inc_cell[gi];
     const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
     const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
     double x[4][3], u[4][3], p[4];
@@ -452,7 +481,7 @@ k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __res
     }
     double blk[16], fr[4];
     const bool row_is_origin = (cm & 3u) == 0;
-    const bool has_bc = cell_bc && cell_bc[cm >> 2];
+    const bool has_bc = has_inc && cell_bc && cell_bc[cm >> 2];
     // lifting needs the Jacobian rows even in a residual-only pass; BC cells are rare, so the branch is cheap
     if (WANT_J) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
     else if (__any_sync(0xffffffffu, has_bc)) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
@@ -460,7 +489,6 @@ k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __res
 
     double lift[4] = {0.0, 0.0, 0.0, 0.0};
     if (has_bc) {
-      // Dirichlet handling at element level (assemble_matrix / apply_lifting semantics)
       const int lj = (j == 0) ? lead[0] : (j == 1) ? lead[1] : (j == 2) ? lead[2] : lead[3];
       int cd[4], rd[4];
       if (contiguous) {
@@ -478,8 +506,8 @@ k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __res
           const double delta = bc_value[cd[d]] - wv[cd[d]];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            if (WANT_F) lift[r] += blk[4 * r + d] * delta;   // lifting with the un-zeroed entry
-            blk[4 * r + d] = 0.0;                              // constrained trial column
+            if (WANT_F) lift[r] += blk[4 * r + d] * delta;
+            blk[4 * r + d] = 0.0;
           }
         }
       }
@@ -487,7 +515,7 @@ k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __res
       for (int r = 0; r < 4; ++r)
         if (bc_marker[rd[r]]) {
 #pragma unroll
-          for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;    // constrained test row
+          for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;
         }
     }
     if (WANT_F) {
@@ -499,62 +527,22 @@ k_p1tet_quad(FormParams form, const double* __restrict__ xg, const double* __res
         const int sw = inc & 3;
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          stageJ[(j * CAP + inc) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
+          v.stageJ[(j * CAP + inc) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
       }
-      if (WANT_F && j == 0) stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
+      if (WANT_F && j == 0) v.stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
     }
   }
+  cp_async_wait_all();
   __syncthreads();
-
-  // ---------------- phase B ----------------
-  if (WANT_F) {
-    const int nF = 16 * h.nent;
-    const double* sf = reinterpret_cast<const double*>(stageF);
-    for (int base = 0; base < nF; base += NT) {
-      const int item = base + tid;
-      const int part = item & 3, r = (item >> 2) & 3, le = item >> 4;
-      double acc = 0.0;
-      if (le < h.nent)
-        for (int ii = s_rel[le].x + part; ii < s_rel[le + 1].x; ii += 4) acc += sf[4 * ii + r];
-      acc = quad_sum(acc);
-      if (le < h.nent && part == 0) {
-        const int4 rd = s_rowdof[le];
-        F[(r == 0) ? rd.x : (r == 1) ? rd.y : (r == 2) ? rd.z : rd.w] = acc;
-      }
-    }
-  }
-  if (WANT_J) {
-    const int nitems = 4 * h.nslots;
-    const uint8_t* srcb = reinterpret_cast<const uint8_t*>(s_src);
-    for (int item = tid; item < nitems; item += NT) {
-      const int ls = item >> 2, r = item & 3;
-      const int le = ent_of_slot[ls];
-      const int2 rel = s_rel[le];
-      const int s = ls - rel.y;
-      const uint8_t* ss = s_ss + ls + le;
-      const int jb = ss[0], je = ss[1];
-      const uint8_t* sp = srcb + 4 * rel.x;
-      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
-      for (int q = jb; q < je; ++q) {
-        const int code = sp[q];
-        const int ii = rel.x + (code >> 2), a = code & 3;
-        const double4 v = stageJ[(a * CAP + ii) * 4 + (r ^ (ii & 3))];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      double* dst = vals + s_rowpos[4 * le + r] + 4 * s;
-      __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
-      __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
-    }
-  }
+  tile_gather<CAP, NT, WANT_J, WANT_F>(v, h, tid, vals, F);
 }
 
 // ------------------------------------------------------------------------------------------ host side
 void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) return;
-  cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_slot_start);
-  cudaFree(P->d_inc_ptr); cudaFree(P->d_slot_ptr); cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_ent);
-  cudaFree(P->d_cell_bc); cudaFree(P->d_tile_hdr); cudaFree(P->d_ent_rel);
+  cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
+  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_cell_bc);
   delete P;
   ctx->p1plan = nullptr;
 }
@@ -565,7 +553,6 @@ void p1tet_mark_bc_dirty(nsgpu_ctx* ctx) {
 
 static bool use_quad(nsgpu_ctx* ctx) { return ctx->lanes == 4; }
 static int plan_cap(nsgpu_ctx* ctx) { return use_quad(ctx) ? ctx->threads / 4 : ctx->threads; }   // incidences per tile
-// launch-bounds pairing: 256 -> 1 CTA/SM, 192 -> 1, 128 -> 2 (all at the full 255-register budget)
 
 bool p1tet_fast_available(nsgpu_ctx* ctx) {
   // valid (lanes, threads) pairs: 1 x {64,128,192,256}; 4 x {256,384,512}
@@ -582,21 +569,22 @@ bool p1tet_fast_available(nsgpu_ctx* ctx) {
 
 static inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n > 0 ? n : 1, 256); }
 
-template <int CAP, int MINB>
-static cudaError_t set_smem_attr() {
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(true)))) return e;
-  if ((e = cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(true)))) return e;
-  return cudaFuncSetAttribute(k_p1tet_tiles<CAP, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAP>::bytes(false));
+template <typename K> static cudaError_t smem_attr(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-template <int CAPI, int MINB>
-static cudaError_t set_smem_attr_quad() {
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(true)))) return e;
-  if ((e = cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(true)))) return e;
-  return cudaFuncSetAttribute(k_p1tet_quad<CAPI, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<CAPI>::bytes(false));
-}
+// the (lanes, threads) -> kernel instantiation table
+#define P1_DISPATCH(OP)                                                                                       \
+  if (lanes == 4) {                                                                                           \
+    if (cap == 128) { OP((k_p1tet_quad<128, 1, true, true>), (k_p1tet_quad<128, 1, true, false>), (k_p1tet_quad<128, 1, false, true>), 128, 512); } \
+    else if (cap == 96) { OP((k_p1tet_quad<96, 1, true, true>), (k_p1tet_quad<96, 1, true, false>), (k_p1tet_quad<96, 1, false, true>), 96, 384); } \
+    else { OP((k_p1tet_quad<64, 2, true, true>), (k_p1tet_quad<64, 2, true, false>), (k_p1tet_quad<64, 2, false, true>), 64, 256); }             \
+  } else {                                                                                                    \
+    if (cap == 256) { OP((k_p1tet_tiles<256, 1, true, true>), (k_p1tet_tiles<256, 1, true, false>), (k_p1tet_tiles<256, 1, false, true>), 256, 256); } \
+    else if (cap == 192) { OP((k_p1tet_tiles<192, 1, true, true>), (k_p1tet_tiles<192, 1, true, false>), (k_p1tet_tiles<192, 1, false, true>), 192, 192); } \
+    else if (cap == 128) { OP((k_p1tet_tiles<128, 2, true, true>), (k_p1tet_tiles<128, 2, true, false>), (k_p1tet_tiles<128, 2, false, true>), 128, 128); } \
+    else { OP((k_p1tet_tiles<64, 4, true, true>), (k_p1tet_tiles<64, 4, true, false>), (k_p1tet_tiles<64, 4, false, true>), 64, 64); }             \
+  }
 
 int p1tet_build_plan(nsgpu_ctx* ctx) {
   cudaStream_t s = ctx->stream;
@@ -607,14 +595,19 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->n_inc = n_inc;
   P->cap = CAPV;
   uint64_t *d_keys = nullptr, *d_keys2 = nullptr, *d_items = nullptr, *d_items2 = nullptr;
-  uint32_t* d_leader = nullptr;
-  int64_t *d_cnt = nullptr, *d_nrun = nullptr, *d_nslots = nullptr, *d_max = nullptr;
+  uint32_t *d_leader = nullptr, *c_cell = nullptr;
+  int4 *c_vtx = nullptr, *c_lead = nullptr;
+  uint8_t *c_src = nullptr, *d_slot_start = nullptr, *d_diag = nullptr;
+  int64_t *d_cnt = nullptr, *d_nrun = nullptr, *d_nslots = nullptr, *d_max = nullptr, *d_inc_ptr = nullptr, *d_slot_ptr = nullptr;
+  int64_t *d_tile_ent = nullptr, *d_tsize = nullptr, *d_boff = nullptr;
   int* d_slot_cnt = nullptr;
   void* d_tmp = nullptr;
   int* d_flag = nullptr;   // [0] bad, [1] not contiguous
   auto cleanup = [&]() {
-    cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_items); cudaFree(d_items2); cudaFree(d_leader); cudaFree(d_cnt);
-    cudaFree(d_nrun); cudaFree(d_nslots); cudaFree(d_max); cudaFree(d_slot_cnt); cudaFree(d_tmp); cudaFree(d_flag);
+    cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_items); cudaFree(d_items2); cudaFree(d_leader); cudaFree(c_cell); cudaFree(c_vtx);
+    cudaFree(c_lead); cudaFree(c_src); cudaFree(d_slot_start); cudaFree(d_diag); cudaFree(d_cnt); cudaFree(d_nrun); cudaFree(d_nslots);
+    cudaFree(d_max); cudaFree(d_inc_ptr); cudaFree(d_slot_ptr); cudaFree(d_tile_ent); cudaFree(d_tsize); cudaFree(d_boff);
+    cudaFree(d_slot_cnt); cudaFree(d_tmp); cudaFree(d_flag);
   };
 #define PL_CUDA(call)                                                                              \
   do {                                                                                             \
@@ -626,8 +619,18 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
       return NSGPU_ECUDA;                                                                          \
     }                                                                                              \
   } while (0)
+#define PL_SCAN(in, out, n)                                                                        \
+  do {                                                                                             \
+    size_t tb__ = 0;                                                                               \
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb__, in, out, n, s));                          \
+    PL_CUDA(cudaMalloc(&d_tmp, tb__));                                                             \
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb__, in, out, n, s));                            \
+    PL_CUDA(cudaStreamSynchronize(s));                                                             \
+    cudaFree(d_tmp); d_tmp = nullptr;                                                              \
+  } while (0)
   if (n_inc == 0) { P->n_tiles = 0; ctx->p1plan = P; return NSGPU_OK; }
 
+  // incidences sorted by row vertex
   PL_CUDA(cudaMalloc(&d_keys, sizeof(uint64_t) * n_inc));
   PL_CUDA(cudaMalloc(&d_keys2, sizeof(uint64_t) * n_inc));
   k_inc_keys<<<g256(n_inc), 256, 0, s>>>(ctx->n_cells_owned, ctx->d_dofmap, d_keys);
@@ -641,7 +644,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   cudaFree(d_tmp); d_tmp = nullptr;
   cudaFree(d_keys); d_keys = nullptr;
 
-  // run-length encode the row vertices -> entity list + incidence counts
+  // run-length encode the row vertices -> vertex list + incidence counts
   PL_CUDA(cudaMalloc(&d_leader, sizeof(uint32_t) * n_inc));
   PL_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (n_inc + 1)));
   PL_CUDA(cudaMalloc(&d_nrun, sizeof(int64_t)));
@@ -656,7 +659,6 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   cudaFree(d_tmp); d_tmp = nullptr;
   P->n_ent = n_ent;
   PL_CUDA(cudaMemsetAsync(d_cnt + n_ent, 0, sizeof(int64_t), s));
-
   PL_CUDA(cudaMalloc(&d_max, sizeof(int64_t)));
   tb = 0;
   PL_CUDA(cub::DeviceReduce::Max(nullptr, tb, d_cnt, d_max, n_ent, s));
@@ -672,44 +674,33 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
     ctx->p1plan = P; p1tet_free(ctx);
     return NSGPU_EUNSUPPORTED;
   }
+  PL_CUDA(cudaMalloc(&d_inc_ptr, sizeof(int64_t) * (n_ent + 1)));
+  PL_SCAN(d_cnt, d_inc_ptr, n_ent + 1);
 
-  PL_CUDA(cudaMalloc(&P->d_inc_ptr, sizeof(int64_t) * (n_ent + 1)));
-  tb = 0;
-  PL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, P->d_inc_ptr, n_ent + 1, s));
-  PL_CUDA(cudaMalloc(&d_tmp, tb));
-  PL_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, P->d_inc_ptr, n_ent + 1, s));
-  PL_CUDA(cudaStreamSynchronize(s));
-  cudaFree(d_tmp); d_tmp = nullptr;
-
-  // per-entity output info and neighbour-slot prefix
+  // per-vertex output info and neighbour-slot prefix
   PL_CUDA(cudaMalloc(&d_flag, 2 * sizeof(int)));
   PL_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), s));
   PL_CUDA(cudaMalloc(&d_nslots, sizeof(int64_t) * (n_ent + 1)));
-  PL_CUDA(cudaMalloc(&P->d_slot_ptr, sizeof(int64_t) * (n_ent + 1)));
+  PL_CUDA(cudaMalloc(&d_slot_ptr, sizeof(int64_t) * (n_ent + 1)));
+  PL_CUDA(cudaMalloc(&d_diag, n_ent + 1));
   PL_CUDA(cudaMalloc(&P->d_rowpos, sizeof(int64_t) * n_ent * 4));
   PL_CUDA(cudaMalloc(&P->d_rowdof, sizeof(int32_t) * n_ent * 4));
-  k_ent_info<<<g256(n_ent + 1), 256, 0, s>>>(n_ent, d_leader, ctx->d_members, ctx->d_pair_first, ctx->d_pair_last, ctx->d_indptr,
-                                             d_nslots, P->d_rowpos, P->d_rowdof, d_flag + 1);
-  tb = 0;
-  PL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nslots, P->d_slot_ptr, n_ent + 1, s));
-  PL_CUDA(cudaMalloc(&d_tmp, tb));
-  PL_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_nslots, P->d_slot_ptr, n_ent + 1, s));
+  k_ent_info<<<g256(n_ent + 1), 256, 0, s>>>(n_ent, d_leader, ctx->d_members, ctx->d_pair_first, ctx->d_pair_last, ctx->d_pairs,
+                                             ctx->d_indptr, d_nslots, P->d_rowpos, P->d_rowdof, d_diag, d_flag + 1);
+  PL_SCAN(d_nslots, d_slot_ptr, n_ent + 1);
   int64_t n_slots = 0;
-  PL_CUDA(cudaMemcpyAsync(&n_slots, P->d_slot_ptr + n_ent, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  PL_CUDA(cudaStreamSynchronize(s));
-  cudaFree(d_tmp); d_tmp = nullptr;
+  PL_CUDA(cudaMemcpy(&n_slots, d_slot_ptr + n_ent, sizeof(int64_t), cudaMemcpyDeviceToHost));
   P->n_slots = n_slots;
 
-  // per-incidence words + gather-list items
-  PL_CUDA(cudaMalloc(&P->d_inc_cell, sizeof(uint32_t) * n_inc));
-  PL_CUDA(cudaMalloc(&P->d_inc_vtx, sizeof(int4) * n_inc));
-  PL_CUDA(cudaMalloc(&P->d_inc_lead, sizeof(int4) * n_inc));
+  // per-incidence words + gather-list items (compact, by sorted incidence index)
+  PL_CUDA(cudaMalloc(&c_cell, sizeof(uint32_t) * n_inc));
+  PL_CUDA(cudaMalloc(&c_vtx, sizeof(int4) * n_inc));
+  PL_CUDA(cudaMalloc(&c_lead, sizeof(int4) * n_inc));
   PL_CUDA(cudaMalloc(&d_items, sizeof(uint64_t) * 4 * n_inc));
   PL_CUDA(cudaMalloc(&d_slot_cnt, sizeof(int) * (n_slots + 1)));
   PL_CUDA(cudaMemsetAsync(d_slot_cnt, 0, sizeof(int) * (n_slots + 1), s));
   k_inc_fill<<<g256(n_inc), 256, 0, s>>>(n_inc, n_ent, d_keys2, ctx->d_cells, ctx->d_dofmap, ctx->d_pairs, ctx->d_pair_first,
-                                         ctx->d_pair_last, P->d_inc_ptr, P->d_slot_ptr, P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead,
-                                         d_items, d_slot_cnt, d_flag);
+                                         ctx->d_pair_last, d_inc_ptr, d_slot_ptr, c_cell, c_vtx, c_lead, d_items, d_slot_cnt, d_flag);
   PL_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_keys2); d_keys2 = nullptr;
   // sort items by (global slot, code): the low bytes in sorted order are the gather lists
@@ -720,26 +711,45 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_items, d_items2, 4 * n_inc, 0, 8 + slot_bits, s));
   PL_CUDA(cudaMalloc(&d_tmp, tb));
   PL_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tb, d_items, d_items2, 4 * n_inc, 0, 8 + slot_bits, s));
-  PL_CUDA(cudaMalloc(&P->d_src, 4 * n_inc));
-  k_item_bytes<<<g256(4 * n_inc), 256, 0, s>>>(4 * n_inc, d_items2, P->d_src);
-  PL_CUDA(cudaMalloc(&P->d_slot_start, n_slots + n_ent + 1));
-  k_slot_start<<<g256(n_ent), 256, 0, s>>>(n_ent, P->d_slot_ptr, d_slot_cnt, P->d_slot_start, d_flag);
+  PL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_tmp); d_tmp = nullptr;
+  cudaFree(d_items); d_items = nullptr;
+  PL_CUDA(cudaMalloc(&c_src, 4 * n_inc));
+  k_item_bytes<<<g256(4 * n_inc), 256, 0, s>>>(4 * n_inc, d_items2, c_src);
+  PL_CUDA(cudaMalloc(&d_slot_start, n_slots + n_ent + 1));
+  k_slot_start<<<g256(n_ent), 256, 0, s>>>(n_ent, d_slot_ptr, d_slot_cnt, d_slot_start, d_flag);
+  PL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_items2); d_items2 = nullptr;
 
-  // tiles: entity e belongs to tile floor(inc_ptr[e] / capeff)
+  // tiles: vertex e belongs to tile floor(inc_ptr[e] / capeff); then the tile-padded / packed arrays
   const int64_t capeff = CAPV - maxdeg + 1;
-  P->n_tiles = ceil_div(n_inc, capeff);
-  PL_CUDA(cudaMalloc(&P->d_tile_ent, sizeof(int64_t) * (P->n_tiles + 1)));
-  k_tiles<<<g256(P->n_tiles + 1), 256, 0, s>>>(P->n_tiles, n_ent, capeff, P->d_inc_ptr, P->d_tile_ent);
-  PL_CUDA(cudaMalloc(&P->d_tile_hdr, sizeof(TileHdr) * P->n_tiles));
+  const int64_t n_tiles = ceil_div(n_inc, capeff);
+  P->n_tiles = n_tiles;
+  PL_CUDA(cudaMalloc(&d_tile_ent, sizeof(int64_t) * (n_tiles + 1)));
+  k_tiles<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, n_ent, capeff, d_inc_ptr, d_tile_ent);
+  PL_CUDA(cudaMalloc(&d_tsize, sizeof(int64_t) * (n_tiles + 1)));
+  PL_CUDA(cudaMalloc(&d_boff, sizeof(int64_t) * (n_tiles + 1)));
+  k_tile_sizes<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, d_tile_ent, d_slot_ptr, d_tsize);
+  PL_SCAN(d_tsize, d_boff, n_tiles + 1);
+  int64_t n_bytes = 0;
+  PL_CUDA(cudaMemcpy(&n_bytes, d_boff + n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  PL_CUDA(cudaMalloc(&P->d_tile_hdr, sizeof(TileHdr) * n_tiles));
   PL_CUDA(cudaMalloc(&P->d_ent_rel, sizeof(int2) * (n_ent + 1)));
-  k_tile_hdr<<<g256(P->n_tiles), 256, 0, s>>>(P->n_tiles, P->d_tile_ent, P->d_inc_ptr, P->d_slot_ptr, P->d_tile_hdr);
-  k_ent_rel<<<(unsigned)P->n_tiles, 64, 0, s>>>(P->n_tiles, P->d_tile_hdr, P->d_inc_ptr, P->d_slot_ptr, P->d_ent_rel);
+  PL_CUDA(cudaMalloc(&P->d_inc_cell, sizeof(uint32_t) * n_tiles * CAPV));
+  PL_CUDA(cudaMalloc(&P->d_inc_vtx, sizeof(int4) * n_tiles * CAPV));
+  PL_CUDA(cudaMalloc(&P->d_inc_lead, sizeof(int4) * n_tiles * CAPV));
+  PL_CUDA(cudaMalloc(&P->d_src, sizeof(uint32_t) * n_tiles * CAPV));
+  PL_CUDA(cudaMalloc(&P->d_tile_bytes, n_bytes + 16));
+  PL_CUDA(cudaMemsetAsync(P->d_tile_bytes, 0, n_bytes + 16, s));
+  k_tile_pack<<<(unsigned)n_tiles, 128, 0, s>>>(CAPV, d_tile_ent, d_inc_ptr, d_slot_ptr, d_boff, c_cell, c_vtx, c_lead,
+                                                reinterpret_cast<const uint32_t*>(c_src), d_slot_start, d_diag, P->d_tile_hdr, P->d_ent_rel,
+                                                P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes);
   PL_CUDA(cudaMalloc(&P->d_cell_bc, ctx->n_cells_owned > 0 ? ctx->n_cells_owned : 1));
   int flags[2] = {0, 0};
   PL_CUDA(cudaMemcpyAsync(flags, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PL_CUDA(cudaStreamSynchronize(s));
   PL_CUDA(cudaGetLastError());
-  ctx->launches += 16;
+  ctx->launches += 18;
   cleanup();
   if (flags[0]) {   // a vertex with too many neighbours / incidences for the byte-packed lists: generic path
     ctx->p1plan = P; p1tet_free(ctx);
@@ -748,40 +758,18 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->contiguous = flags[1] == 0;
   P->bc_dirty = true;
   ctx->p1plan = P;
+  const int lanes = ctx->lanes, cap = CAPV;
   cudaError_t e = cudaSuccess;
-  if (use_quad(ctx)) e = CAPV == 128 ? set_smem_attr_quad<128, 1>() : (CAPV == 96 ? set_smem_attr_quad<96, 1>() : set_smem_attr_quad<64, 2>());
-  else e = CAPV == 256 ? set_smem_attr<256, 1>() : (CAPV == 192 ? set_smem_attr<192, 1>() : (CAPV == 128 ? set_smem_attr<128, 2>() : set_smem_attr<64, 4>()));
+#define P1_ATTR(KJF, KJ, KF, CAPC, NTC)                                                      \
+  if (e == cudaSuccess) e = smem_attr(KJF, TileSmem<CAPC>::bytes(true));                      \
+  if (e == cudaSuccess) e = smem_attr(KJ, TileSmem<CAPC>::bytes(true));                       \
+  if (e == cudaSuccess) e = smem_attr(KF, TileSmem<CAPC>::bytes(false));
+  P1_DISPATCH(P1_ATTR)
+#undef P1_ATTR
   if (e != cudaSuccess) { set_error(ctx, std::string("p1tet plan: smem attribute: ") + cudaGetErrorString(e)); p1tet_free(ctx); return NSGPU_ECUDA; }
   return NSGPU_OK;
 #undef PL_CUDA
-}
-
-template <int CAP, int MINB>
-static void launch_tiles(nsgpu_ctx* ctx, nsgpu_p1tet_plan* P, const double* d_xin, bool want_J, bool want_F, double* d_Fout, const uint8_t* cbc) {
-  cudaStream_t s = ctx->stream;
-#define P1_LAUNCH(J, F)                                                                                              \
-  k_p1tet_tiles<CAP, MINB, J, F><<<(unsigned)P->n_tiles, CAP, TileSmem<CAP>::bytes(J), s>>>(ctx->form, ctx->d_x, d_xin,   \
-      ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead,  \
-      reinterpret_cast<const uint32_t*>(P->d_src), P->d_slot_start, P->d_ent_rel, P->d_rowpos,                            \
-      reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout)
-  if (want_J && want_F) P1_LAUNCH(true, true);
-  else if (want_J) P1_LAUNCH(true, false);
-  else P1_LAUNCH(false, true);
-#undef P1_LAUNCH
-}
-
-template <int CAPI, int MINB>
-static void launch_quad(nsgpu_ctx* ctx, nsgpu_p1tet_plan* P, const double* d_xin, bool want_J, bool want_F, double* d_Fout, const uint8_t* cbc) {
-  cudaStream_t s = ctx->stream;
-#define P1Q_LAUNCH(J, F)                                                                                             \
-  k_p1tet_quad<CAPI, MINB, J, F><<<(unsigned)P->n_tiles, 4 * CAPI, TileSmem<CAPI>::bytes(J), s>>>(ctx->form, ctx->d_x, d_xin,   \
-      ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead,  \
-      reinterpret_cast<const uint32_t*>(P->d_src), P->d_slot_start, P->d_ent_rel, P->d_rowpos,                            \
-      reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout)
-  if (want_J && want_F) P1Q_LAUNCH(true, true);
-  else if (want_J) P1Q_LAUNCH(true, false);
-  else P1Q_LAUNCH(false, true);
-#undef P1Q_LAUNCH
+#undef PL_SCAN
 }
 
 int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
@@ -795,14 +783,17 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
     ctx->launches += 1;
   }
   const uint8_t* cbc = ctx->has_bc ? P->d_cell_bc : nullptr;
-  if (use_quad(ctx)) {
-    if (P->cap == 128) launch_quad<128, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-    else if (P->cap == 96) launch_quad<96, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-    else launch_quad<64, 2>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-  } else if (P->cap == 256) launch_tiles<256, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-  else if (P->cap == 192) launch_tiles<192, 1>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-  else if (P->cap == 128) launch_tiles<128, 2>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
-  else launch_tiles<64, 4>(ctx, P, d_xin, want_J, want_F, d_Fout, cbc);
+  const int lanes = ctx->lanes, cap = P->cap;
+#define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, \
+                P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
+                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout
+#define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
+  if (want_J && want_F) KJF<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);        \
+  else if (want_J) KJ<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);              \
+  else KF<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(false), s>>>(P1_ARGS);
+  P1_DISPATCH(P1_RUN)
+#undef P1_RUN
+#undef P1_ARGS
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
   return NSGPU_OK;
