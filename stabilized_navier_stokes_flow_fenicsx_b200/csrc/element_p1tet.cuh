@@ -198,6 +198,187 @@ NS_HD void p1tet_rowslab(const FormParams& fp, const bool row_is_origin, const d
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Register-lean version of p1tet_rowslab (what the CUDA kernel runs).  Same algebra, reorganised so that
+//   * everything that does not depend on the column vertex n is folded once into C0 (3x3), P0 (3) and a few scalars:
+//       A_vv[c][d] = C0[c][d] + [n == 0] e^2 W D[c][d] + L Q[c][d] + uq_n[c] t1[d] + g_0[c] t2[d] + delta_cd dia
+//       A_pv[d]    = P0[d] + W g_n[d] + t1[d] + s[d] L
+//     with t1 = e W tau_n (H - tau_n^2 a_0(n) Gu_n),  t2 = e W tau_n kappa Gu_n + nuL g_n   (per block: ~70 FMA);
+//   * the per-point data of points 1..3 is parked by `scratch` (the kernel uses the thread's own, not yet written,
+//     staging slots in shared memory) and fetched back right before the block that needs it;
+//   * each finished 4x4 block is handed to `emit(n, blk)` immediately (Dirichlet handling + staging store).
+// Live state during the block loop is ~55 doubles instead of ~100, which gives ptxas room to interleave the
+// independent FMA chains (the fp64 pipe needs ILP >= 2 at 8 warps/SM: tools/microbench.cu).
+struct P1TetPoint { double uq[3], Gu[3], ew, eb, ea; };   // ew = e W tau, eb = e W tau^3 a_0, ea = e W tau a_0
+
+template <bool WANT_J, bool WANT_F, class Scratch, class Emit>
+NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const double (&x)[4][3], const double (&u)[4][3],
+                          const double (&p)[4], double (&fr)[4], Scratch&& scratch, Emit&& emit) {
+  double J[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) J[i][j] = x[j + 1][i] - x[0][i];
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double idet = 1.0 / det;
+  double g[4][3];
+  g[1][0] = c00 * idet; g[2][0] = c01 * idet; g[3][0] = c02 * idet;
+  g[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet;
+  g[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet;
+  g[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet;
+  g[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
+  g[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
+  g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) g[0][j] = -(g[1][j] + g[2][j] + g[3][j]);
+  const double W = fabs(det) * (1.0 / 24.0);
+  const double V = 4.0 * W;
+
+  double G[6], gk[3];   // G: xx xy xz yy yz zz (sum over the three non-origin vertices)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) gk[j] = row_is_origin ? g[1][j] : g[0][j];
+  G[0] = gk[0] * gk[0] + g[2][0] * g[2][0] + g[3][0] * g[3][0];
+  G[1] = gk[0] * gk[1] + g[2][0] * g[2][1] + g[3][0] * g[3][1];
+  G[2] = gk[0] * gk[2] + g[2][0] * g[2][2] + g[3][0] * g[3][2];
+  G[3] = gk[1] * gk[1] + g[2][1] * g[2][1] + g[3][1] * g[3][1];
+  G[4] = gk[1] * gk[2] + g[2][1] * g[2][2] + g[3][1] * g[3][2];
+  G[5] = gk[2] * gk[2] + g[2][2] * g[2][2] + g[3][2] * g[3][2];
+  const double trG = G[0] + G[3] + G[5];
+  const double Cst = fp.Ci * fp.nu * fp.nu * (G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]));
+  const double itrG = 1.0 / trG;
+
+  double D[3][3], P[3], U[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    U[i] = u[0][i] + u[1][i] + u[2][i] + u[3][i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) D[i][j] = u[0][i] * g[0][j] + u[1][i] * g[1][j] + u[2][i] * g[2][j] + u[3][i] * g[3][j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) P[j] = p[0] * g[0][j] + p[1] * g[1][j] + p[2] * g[2][j] + p[3] * g[3][j];
+  const double divu = D[0][0] + D[1][1] + D[2][2];
+
+  // ---- quadrature points: totals stay in registers, the data of points 1..3 is parked ----
+  double s[3] = {0, 0, 0}, Q[6] = {0, 0, 0, 0, 0, 0}, ZG[3] = {0, 0, 0}, TR[3] = {0, 0, 0}, Y3[3] = {0, 0, 0}, sup[3] = {0, 0, 0};
+  double Y1[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double tbar = 0.0, nuLbar = 0.0;
+  P1TetPoint pt0;
+  double ub[3];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    P1TetPoint pt;
+    double r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pt.uq[i] = P1T_A * U[i] + P1T_E * u[q][i];
+    pt.Gu[0] = G[0] * pt.uq[0] + G[1] * pt.uq[1] + G[2] * pt.uq[2];
+    pt.Gu[1] = G[1] * pt.uq[0] + G[3] * pt.uq[1] + G[4] * pt.uq[2];
+    pt.Gu[2] = G[2] * pt.uq[0] + G[4] * pt.uq[1] + G[5] * pt.uq[2];
+    const double arg = Cst + pt.uq[0] * pt.Gu[0] + pt.uq[1] * pt.Gu[1] + pt.uq[2] * pt.Gu[2];
+    const double tau = NS_RSQRT(arg);
+    const double wt = W * tau;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] = P[j] + pt.uq[0] * D[0][j] + pt.uq[1] * D[1][j] + pt.uq[2] * D[2][j];
+    const double al = wt * (r[0] * g[0][0] + r[1] * g[0][1] + r[2] * g[0][2]);
+    const double be = al * tau * tau;
+    pt.ew = P1T_E * wt; pt.eb = P1T_E * be; pt.ea = P1T_E * al;
+    tbar += wt;
+    nuLbar += wt * arg;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s[i] += wt * pt.uq[i];
+      ZG[i] += wt * pt.Gu[i];
+      TR[i] += wt * r[i];
+      Y3[i] += be * pt.Gu[i];
+      if (WANT_F) sup[i] += al * pt.uq[i];
+    }
+    {
+      const double w0 = wt * pt.uq[0], w1 = wt * pt.uq[1], w2 = wt * pt.uq[2];
+      Q[0] += w0 * pt.uq[0]; Q[1] += w0 * pt.uq[1]; Q[2] += w0 * pt.uq[2];
+      Q[3] += w1 * pt.uq[1]; Q[4] += w1 * pt.uq[2]; Q[5] += w2 * pt.uq[2];
+    }
+    if (WANT_J) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double bg = be * pt.Gu[d];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Y1[d][c] += bg * pt.uq[c];
+      }
+    }
+    if (q == 0) {
+      pt0 = pt;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) ub[d] = W * (P1T_A * U[d] + P1T_E * pt.uq[d]);   // sum_q W N_0(q) u_q
+    } else if (WANT_J) {
+      scratch.put(q, pt);
+    }
+  }
+  nuLbar *= itrG;
+
+  double H[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) H[d] = D[d][0] * g[0][0] + D[d][1] * g[0][1] + D[d][2] * g[0][2];
+  const double TR0 = TR[0] * g[0][0] + TR[1] * g[0][1] + TR[2] * g[0][2];
+
+  if (WANT_F) {
+    const double pbarV = W * (p[0] + p[1] + p[2] + p[3]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      fr[c] = D[c][0] * ub[0] + D[c][1] * ub[1] + D[c][2] * ub[2] + fp.nu * V * H[c] - pbarV * g[0][c] + sup[c] + nuLbar * divu * g[0][c];
+    fr[3] = W * divu + TR0;
+  }
+
+  if (WANT_J) {
+    const double kap = divu * itrG;
+    const double M_off = W * (4.0 * P1T_A * P1T_A + 2.0 * P1T_A * P1T_E);
+    const double akap = P1T_A * kap;
+    // column-vertex independent parts
+    double C0[3][3], P0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        C0[c][d] = M_off * D[c][d] + P1T_A * (s[c] * H[d] - Y1[d][c]) + akap * ZG[d] * g[0][c];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) P0[d] = P1T_A * (tbar * H[d] - Y3[d]);
+    const double dia0 = P1T_A * TR0;
+    const double nuV = fp.nu * V;
+    const double Qm[3][3] = {{Q[0], Q[1], Q[2]}, {Q[1], Q[3], Q[4]}, {Q[2], Q[4], Q[5]}};
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      P1TetPoint pt;
+      if (n == 0) pt = pt0; else scratch.get(n, pt);
+      const double L = g[0][0] * g[n][0] + g[0][1] * g[n][1] + g[0][2] * g[n][2];
+      double t1[3], t2[3];
+      const double ewk = pt.ew * kap;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        t1[d] = pt.ew * H[d] - pt.eb * pt.Gu[d];
+        t2[d] = ewk * pt.Gu[d] + nuLbar * g[n][d];
+      }
+      const double dia = ub[0] * g[n][0] + ub[1] * g[n][1] + ub[2] * g[n][2] + nuV * L + dia0 + pt.ea;
+      double blk[16];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double v = C0[c][d] + L * Qm[c][d] + pt.uq[c] * t1[d] + g[0][c] * t2[d];
+          if (n == 0) v += (W * P1T_E * P1T_E) * D[c][d];
+          if (c == d) v += dia;
+          blk[4 * c + d] = v;
+        }
+        blk[4 * c + 3] = s[c] * L - W * g[0][c];
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) blk[12 + d] = P0[d] + W * g[n][d] + t1[d] + s[d] * L;
+      blk[15] = tbar * L;
+      emit(n, blk);
+    }
+  }
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------
 // Quad-lane version of the same algebra: the four lanes of an aligned lane quad share one incidence.

@@ -434,6 +434,8 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     NS_REQUIRE(ctx, value == 64 || value == 128 || value == 192 || value == 256 || value == 384 || value == 512,
                "set_option: threads must be 64, 128, 192, 256, 384 or 512");
     ctx->threads = (int)value;
+  } else if (!strcmp(name, "debug")) {
+    ctx->debug = (int)value;
   } else if (!strcmp(name, "lanes")) {
     NS_REQUIRE(ctx, value == 1 || value == 4, "set_option: lanes must be 1 or 4");
     ctx->lanes = (int)value;

@@ -290,11 +290,10 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
   const uint8_t* eos = v.bytes + pad16(h.nslots + h.nent + 1);
   const uint8_t* dg = eos + pad16(h.nslots);
   if (WANT_J) {
-    // off-diagonal slots: one (slot, row) piece per thread, 4-6 parked blocks each
-    const int nitems = 4 * h.nslots;
+    // off-diagonal slots: one slot (all four rows, 16 accumulators) per thread, 4-6 parked blocks each; the list
+    // decode is shared by the four rows and consecutive lanes write consecutive 32-byte pieces of each row
     const uint8_t* srcb = reinterpret_cast<const uint8_t*>(v.src);
-    for (int item = tid; item < nitems; item += NT) {
-      const int ls = item >> 2, r = item & 3;
+    for (int ls = tid; ls < h.nslots; ls += NT) {
       const int le = eos[ls];
       const int2 rel = v.rel[le];
       const int s = ls - rel.y;
@@ -302,16 +301,26 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
       const uint8_t* ss = s_ss + ls + le;
       const int jb = ss[0], je = ss[1];
       const uint8_t* sp = srcb + 4 * rel.x;
-      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+      double4 acc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = make_double4(0.0, 0.0, 0.0, 0.0);
       for (int q = jb; q < je; ++q) {
         const int code = sp[q];
         const int ii = rel.x + (code >> 2), a = code & 3;
-        const double4 w = v.stageJ[(a * CAP + ii) * 4 + (r ^ (ii & 3))];
-        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+        const double4* blkp = v.stageJ + (a * CAP + ii) * 4;
+        const int sw = ii & 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double4 w = blkp[r ^ sw];
+          acc[r].x += w.x; acc[r].y += w.y; acc[r].z += w.z; acc[r].w += w.w;
+        }
       }
-      double* dst = vals + v.rowpos[4 * le + r] + 4 * s;
-      __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
-      __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double* dst = vals + v.rowpos[4 * le + r] + 4 * s;
+        __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[r].x, acc[r].y));
+        __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc[r].z, acc[r].w));
+      }
     }
   }
   {
@@ -356,7 +365,7 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
       const uint8_t *__restrict__ cell_bc, const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,              \
       const int4 *__restrict__ inc_lead, const uint32_t *__restrict__ src, const uint8_t *__restrict__ tile_bytes,               \
       const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
-      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F
+      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg
 
 // one thread per incidence
 template <int CAP, int MINB, bool WANT_J, bool WANT_F>
@@ -381,6 +390,12 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const double* xp = xg + 3 * (int64_t)vtx[a];
+      if (dbg & 4) {
+        x[a][0] = vtx[a]; x[a][1] = a; x[a][2] = lead[a]; u[a][0] = 1; u[a][1] = 2; u[a][2] = 3; p[a] = 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dof[a][c] = lead[a] + c;
+        continue;
+      }
       x[a][0] = xp[0]; x[a][1] = xp[1]; x[a][2] = xp[2];
       if (contiguous) {
         const double2* wp = reinterpret_cast<const double2*>(wv + lead[a]);
@@ -394,54 +409,83 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
         u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
       }
     }
-    double blk[4][16], fr[4];
+    double fr[4] = {0.0, 0.0, 0.0, 0.0};
     const bool row_is_origin = (cm & 3u) == 0;
     const bool has_bc = cell_bc && cell_bc[cm >> 2];
-    if (WANT_J || !has_bc) p1tet_rowslab<WANT_J, WANT_F>(form, row_is_origin, x, u, p, blk, fr);
-    else p1tet_rowslab<true, WANT_F>(form, row_is_origin, x, u, p, blk, fr);   // residual only, but lifting needs the Jacobian rows
-
+    bool rowbc[4] = {false, false, false, false};
     if (has_bc) {
-      // Dirichlet handling at element level (assemble_matrix / apply_lifting semantics)
-      bool rowbc[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) rowbc[r] = bc_marker[dof[0][r]] != 0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
+    }
+    const int sw = tid & 3;
+    // finished block n: Dirichlet handling at element level (assemble_matrix / apply_lifting semantics),
+    // then straight into the thread's staging slot
+    auto emit = [&](const int n, double (&blk)[16]) {
+      if (has_bc) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          const int32_t dj = dof[a][d];
+          const int32_t dj = dof[n][d];
           if (bc_marker[dj]) {
-            const double delta = bc_value[dj] - ((d < 3) ? u[a][d] : p[a]);
+            const double delta = bc_value[dj] - ((d < 3) ? u[n][d] : p[n]);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              if (WANT_F) fr[r] += blk[a][4 * r + d] * delta;   // lifting with the un-zeroed entry
-              if (WANT_J) blk[a][4 * r + d] = 0.0;               // constrained trial column
+              if (WANT_F) fr[r] += blk[4 * r + d] * delta;   // lifting with the un-zeroed entry
+              blk[4 * r + d] = 0.0;                            // constrained trial column
             }
           }
         }
-      if (WANT_J) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
           if (rowbc[r]) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int d = 0; d < 4; ++d) blk[a][4 * r + d] = 0.0;   // constrained test row
+            for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;  // constrained test row
           }
       }
-    }
-    if (WANT_J) {
-      const int sw = tid & 3;
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
+      if (WANT_J) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          v.stageJ[(a * CAP + tid) * 4 + (r ^ sw)] = make_double4(blk[a][4 * r], blk[a][4 * r + 1], blk[a][4 * r + 2], blk[a][4 * r + 3]);
+          v.stageJ[(n * CAP + tid) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
+      }
+    };
+    if (WANT_J) {
+      // point data of q = 1..3 waits in the (not yet written) staging slot of block q
+      struct SmemScratch {
+        double4* base; int sw;
+        __device__ void put(int q, const P1TetPoint& pt) const {
+          double4* s = base + q * CAP * 4;
+          s[0 ^ sw] = make_double4(pt.uq[0], pt.uq[1], pt.uq[2], pt.Gu[0]);
+          s[1 ^ sw] = make_double4(pt.Gu[1], pt.Gu[2], pt.ew, pt.eb);
+          s[2 ^ sw] = make_double4(pt.ea, 0.0, 0.0, 0.0);
+        }
+        __device__ void get(int q, P1TetPoint& pt) const {
+          const double4* s = base + q * CAP * 4;
+          const double4 a = s[0 ^ sw], b = s[1 ^ sw], c = s[2 ^ sw];
+          pt.uq[0] = a.x; pt.uq[1] = a.y; pt.uq[2] = a.z; pt.Gu[0] = a.w;
+          pt.Gu[1] = b.x; pt.Gu[2] = b.y; pt.ew = b.z; pt.eb = b.w; pt.ea = c.x;
+        }
+      } scratch{v.stageJ + tid * 4, sw};
+      if (dbg & 2) {   // timing experiment: no algebra
+        double z[16] = {x[0][0] + u[1][1] + p[2] + x[3][2] + u[3][0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) emit(n, z);
+      } else {
+        p1tet_rowslab2<true, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
+      }
+    } else {
+      // residual-only pass: the Jacobian rows are needed only for the lifting term of cells that touch a Dirichlet dof
+      struct LocalScratch {
+        P1TetPoint q[4];
+        __device__ void put(int i, const P1TetPoint& pt) { q[i] = pt; }
+        __device__ void get(int i, P1TetPoint& pt) const { pt = q[i]; }
+      } scratch;
+      if (has_bc) p1tet_rowslab2<true, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
+      else p1tet_rowslab2<false, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
     }
     if (WANT_F) v.stageF[tid] = make_double4(fr[0], fr[1], fr[2], fr[3]);
   }
   cp_async_wait_all();
   __syncthreads();
+  if (dbg & 1) return;
   tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
 }
 
@@ -786,7 +830,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   const int lanes = ctx->lanes, cap = P->cap;
 #define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
-                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout
+                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug
 #define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
   if (want_J && want_F) KJF<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);        \
   else if (want_J) KJ<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);              \

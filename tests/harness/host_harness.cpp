@@ -56,3 +56,31 @@ extern "C" int harness_p1tet(double nu, double Ci, const double* x, const double
   }
   return 0;
 }
+
+// Same reconstruction through the register-lean variant (scratch and emit are plain arrays on the host).
+extern "C" int harness_p1tet2(double nu, double Ci, const double* x, const double* w, double* Ae, double* be) {
+  FormParams f{0, nu, Ci, 1.0, 1.0, 0.0};
+  for (int m = 0; m < 4; ++m) {
+    int perm[4] = {m, 0, 0, 0};
+    for (int k = 0, j = 1; k < 4; ++k) if (k != m) perm[j++] = k;
+    double xx[4][3], uu[4][3], pp[4], fr[4];
+    for (int a = 0; a < 4; ++a) {
+      for (int i = 0; i < 3; ++i) { xx[a][i] = x[3 * perm[a] + i]; uu[a][i] = w[3 * perm[a] + i]; }
+      pp[a] = w[12 + perm[a]];
+    }
+    struct Scratch { P1TetPoint q[4]; void put(int i, const P1TetPoint& p) { q[i] = p; } void get(int i, P1TetPoint& p) const { p = q[i]; } } sc;
+    double blks[4][16];
+    auto emit = [&](int n, const double (&b)[16]) { for (int k = 0; k < 16; ++k) blks[n][k] = b[k]; };
+    p1tet_rowslab2<true, true>(f, m == 0, xx, uu, pp, fr, sc, emit);
+    for (int r = 0; r < 4; ++r) {
+      const int row = r < 3 ? 3 * m + r : 12 + m;
+      be[row] = fr[r];
+      for (int a = 0; a < 4; ++a)
+        for (int d = 0; d < 4; ++d) {
+          const int col = d < 3 ? 3 * perm[a] + d : 12 + perm[a];
+          Ae[row * 16 + col] = blks[a][4 * r + d];
+        }
+    }
+  }
+  return 0;
+}

@@ -17,6 +17,32 @@ __global__ void k_dfma(double* out, int iters, double a, double b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// DFMA throughput as a function of instruction-level parallelism (independent chains per thread) and warps per SM
+template <int ILP>
+__global__ void k_dfma_ilp(double* out, int iters, double a, double b) {
+  double x[ILP];
+#pragma unroll
+  for (int k = 0; k < ILP; ++k) x[k] = threadIdx.x + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) x[k] = fma(x[k], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < ILP; ++k) s += x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int ILP>
+static void run_ilp(double* out, int warps_per_sm, cudaEvent_t e0, cudaEvent_t e1, int sms, double clk_hz) {
+  const int iters = 20000;
+  k_dfma_ilp<ILP><<<sms, 32 * warps_per_sm>>>(out, 10, 1.0000001, 1e-9);
+  cudaEventRecord(e0); k_dfma_ilp<ILP><<<sms, 32 * warps_per_sm>>>(out, iters, 1.0000001, 1e-9); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double fma = (double)ILP * iters * sms * 32.0 * warps_per_sm;
+  printf("  warps/SM %2d ILP %d: %.1f DFMA/clk/SM\n", warps_per_sm, ILP, fma / (ms * 1e-3) / sms / clk_hz);
+}
+
 __device__ __forceinline__ uint64_t mix(uint64_t z) {
   z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33; return z;
 }
@@ -75,6 +101,14 @@ int main() {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double fl = 2.0 * 8 * iters * (double)blocks * threads;
     printf("DFMA: %.2f TFLOP/s  (%.1f DFMA/clk/SM at %.0f MHz nominal)\n", fl / ms / 1e9, fl / 2 / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1e3);
+  }
+  {
+    printf("DFMA issue vs occupancy / ILP (peak = 64 per clk per SM):\n");
+    for (int w : {4, 8, 16, 32}) {
+      run_ilp<1>(out, w, e0, e1, p.multiProcessorCount, p.clockRate * 1e3);
+      run_ilp<2>(out, w, e0, e1, p.multiProcessorCount, p.clockRate * 1e3);
+      run_ilp<4>(out, w, e0, e1, p.multiProcessorCount, p.clockRate * 1e3);
+    }
   }
   {
     const uint64_t n = 1ull << 28;  // 2 GiB of doubles
