@@ -51,6 +51,7 @@ int nsgpu_create(nsgpu_ctx** out, int device) {
   nsgpu_ctx* ctx = new (std::nothrow) nsgpu_ctx();
   if (!ctx) return NSGPU_EINVAL;
   ctx->device = device;
+  { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) ctx->n_sms = pr.multiProcessorCount; }
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev[1])) != cudaSuccess) {
     set_error(nullptr, std::string("context creation: ") + cudaGetErrorString(e));
@@ -434,6 +435,8 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     NS_REQUIRE(ctx, value == 64 || value == 128 || value == 192 || value == 256 || value == 384 || value == 512,
                "set_option: threads must be 64, 128, 192, 256, 384 or 512");
     ctx->threads = (int)value;
+  } else if (!strcmp(name, "persistent")) {
+    ctx->persistent = value != 0;
   } else if (!strcmp(name, "debug")) {
     ctx->debug = (int)value;
   } else if (!strcmp(name, "lanes")) {

@@ -365,7 +365,7 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
       const uint8_t *__restrict__ cell_bc, const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,              \
       const int4 *__restrict__ inc_lead, const uint32_t *__restrict__ src, const uint8_t *__restrict__ tile_bytes,               \
       const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
-      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg
+      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg, const int64_t n_tiles
 
 // one thread per incidence
 template <int CAP, int MINB, bool WANT_J, bool WANT_F>
@@ -373,13 +373,15 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const TileView<CAP, WANT_J> v(smem_raw);
   const int tid = threadIdx.x;
-  const int64_t tile = blockIdx.x;
+  // persistent CTAs: the grid is a few CTAs per SM, each walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  // (a fresh CTA per tile costs ~1.4 us of launch/teardown per tile on B200, as much as the tile's own work)
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   // phase-A inputs are tile-padded: their loads do not depend on the header
   const int4 vt = inc_vtx[tile * CAP + tid];
   const int4 ld = inc_lead[tile * CAP + tid];
   const uint32_t cm = inc_cell[tile * CAP + tid];
   const TileHdr h = tile_hdr[tile];
-  if (h.nent <= 0) return;
+  if (h.nent <= 0) continue;
   tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
 
   if (tid < h.ninc) {
@@ -485,8 +487,9 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
   }
   cp_async_wait_all();
   __syncthreads();
-  if (dbg & 1) return;
-  tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+  if (!(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+  __syncthreads();   // staging and tables are reused by the next tile
+  }
 }
 
 // four lanes per incidence (p1tet_quad): a tile of CAPI incidences is a CTA of 4 * CAPI threads
@@ -830,11 +833,14 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   const int lanes = ctx->lanes, cap = P->cap;
 #define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
-                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug
+                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles
+  // one-thread kernels are persistent (grid = resident CTAs); the quad kernels take one tile per CTA
+  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 64 ? 4 : 1));
+  const unsigned grid = (unsigned)((lanes == 4 || ctx->persistent == 0) ? P->n_tiles : (resident < P->n_tiles ? resident : P->n_tiles));
 #define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
-  if (want_J && want_F) KJF<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);        \
-  else if (want_J) KJ<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);              \
-  else KF<<<(unsigned)P->n_tiles, NTC, TileSmem<CAPC>::bytes(false), s>>>(P1_ARGS);
+  if (want_J && want_F) KJF<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                        \
+  else if (want_J) KJ<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                              \
+  else KF<<<grid, NTC, TileSmem<CAPC>::bytes(false), s>>>(P1_ARGS);
   P1_DISPATCH(P1_RUN)
 #undef P1_RUN
 #undef P1_ARGS
