@@ -224,7 +224,7 @@ __global__ void k_cell_bc(int64_t n_cells, const int32_t* __restrict__ dofmap, c
 
 // ------------------------------------------------------------------------------------------ the kernels
 template <int CAP> struct TileSmem {
-  // stageJ [4 blocks][CAP][4 rows] double4 (row index swizzled by incidence) | stageF [CAP] double4 |
+  // stageJ [4 blocks][8 pieces][CAP] double2 (piece k = 2 * row + half; incidence-minor: conflict-free writes) | stageF [CAP] double4 |
   // rowpos [CAP][4] i64 | rowdof [CAP] int4 | rel [CAP+2] int2 | src [CAP] u32 | byte tables
   static constexpr int kBytes = ((5 * CAP + 1 + 15) & ~15) + ((4 * CAP + 15) & ~15) + ((CAP + 15) & ~15);
   static constexpr size_t stageJ = 16 * (size_t)CAP * sizeof(double4);
@@ -234,10 +234,10 @@ template <int CAP> struct TileSmem {
 };
 
 template <int CAP, bool WANT_J> struct TileView {
-  double4* stageJ; double4* stageF; int64_t* rowpos; int4* rowdof; int2* rel; uint32_t* src; uint8_t* bytes;
+  double2* stageJ; double4* stageF; int64_t* rowpos; int4* rowdof; int2* rel; uint32_t* src; uint8_t* bytes;
   __device__ explicit TileView(unsigned char* raw) {
-    stageJ = reinterpret_cast<double4*>(raw);
-    stageF = stageJ + (WANT_J ? 16 * CAP : 0);
+    stageJ = reinterpret_cast<double2*>(raw);
+    stageF = reinterpret_cast<double4*>(stageJ + (WANT_J ? 32 * CAP : 0));
     rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
     rowdof = reinterpret_cast<int4*>(rowpos + 4 * CAP);
     rel = reinterpret_cast<int2*>(rowdof + CAP);
@@ -307,12 +307,11 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
       for (int q = jb; q < je; ++q) {
         const int code = sp[q];
         const int ii = rel.x + (code >> 2), a = code & 3;
-        const double4* blkp = v.stageJ + (a * CAP + ii) * 4;
-        const int sw = ii & 3;
+        const double2* blkp = v.stageJ + a * 8 * CAP + ii;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double4 w = blkp[r ^ sw];
-          acc[r].x += w.x; acc[r].y += w.y; acc[r].z += w.z; acc[r].w += w.w;
+          const double2 lo = blkp[(2 * r) * CAP], hi = blkp[(2 * r + 1) * CAP];
+          acc[r].x += lo.x; acc[r].y += lo.y; acc[r].z += hi.x; acc[r].w += hi.y;
         }
       }
 #pragma unroll
@@ -328,7 +327,7 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
     const int nD = 16 * h.nent;
     const double* sf = reinterpret_cast<const double*>(v.stageF);
     for (int base = 0; base < nD; base += NT) {
-      const int item = base + tid;
+      const int item = base + (NT - 1 - tid);          // from the top: the warps with no slot work above start here at once
       const int part = item & 3, r = (item >> 2) & 3, le = item >> 4;
       double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
       double accF = 0.0;
@@ -336,8 +335,8 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
         const int ib = v.rel[le].x, ie = v.rel[le + 1].x;
         for (int ii = ib + part; ii < ie; ii += 4) {
           if (WANT_J) {
-            const double4 w = v.stageJ[ii * 4 + (r ^ (ii & 3))];
-            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+            const double2 lo = v.stageJ[(2 * r) * CAP + ii], hi = v.stageJ[(2 * r + 1) * CAP + ii];
+            acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
           }
           if (WANT_F) accF += sf[4 * ii + r];
         }
@@ -443,29 +442,32 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
             for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;  // constrained test row
           }
       }
-      if (WANT_J) {
+      if (WANT_J && !((dbg & 8) && blk[0] != 123.456)) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          v.stageJ[(n * CAP + tid) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
+        {
+          v.stageJ[(n * 8 + 2 * r) * CAP + tid] = make_double2(blk[4 * r], blk[4 * r + 1]);
+          v.stageJ[(n * 8 + 2 * r + 1) * CAP + tid] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
+        }
       }
     };
     if (WANT_J) {
       // point data of q = 1..3 waits in the (not yet written) staging slot of block q
       struct SmemScratch {
-        double4* base; int sw;
+        double2* base;   // this thread's column of the staging area: piece (q, k) at base[(q * 8 + k) * CAP]
         __device__ void put(int q, const P1TetPoint& pt) const {
-          double4* s = base + q * CAP * 4;
-          s[0 ^ sw] = make_double4(pt.uq[0], pt.uq[1], pt.uq[2], pt.Gu[0]);
-          s[1 ^ sw] = make_double4(pt.Gu[1], pt.Gu[2], pt.ew, pt.eb);
-          s[2 ^ sw] = make_double4(pt.ea, 0.0, 0.0, 0.0);
+          double2* s = base + q * 8 * CAP;
+          s[0] = make_double2(pt.uq[0], pt.uq[1]); s[CAP] = make_double2(pt.uq[2], pt.Gu[0]);
+          s[2 * CAP] = make_double2(pt.Gu[1], pt.Gu[2]); s[3 * CAP] = make_double2(pt.ew, pt.eb);
+          s[4 * CAP] = make_double2(pt.ea, 0.0);
         }
         __device__ void get(int q, P1TetPoint& pt) const {
-          const double4* s = base + q * CAP * 4;
-          const double4 a = s[0 ^ sw], b = s[1 ^ sw], c = s[2 ^ sw];
-          pt.uq[0] = a.x; pt.uq[1] = a.y; pt.uq[2] = a.z; pt.Gu[0] = a.w;
-          pt.Gu[1] = b.x; pt.Gu[2] = b.y; pt.ew = b.z; pt.eb = b.w; pt.ea = c.x;
+          const double2* s = base + q * 8 * CAP;
+          const double2 a = s[0], b = s[CAP], c = s[2 * CAP], d = s[3 * CAP], e = s[4 * CAP];
+          pt.uq[0] = a.x; pt.uq[1] = a.y; pt.uq[2] = b.x; pt.Gu[0] = b.y;
+          pt.Gu[1] = c.x; pt.Gu[2] = c.y; pt.ew = d.x; pt.eb = d.y; pt.ea = e.x;
         }
-      } scratch{v.stageJ + tid * 4, sw};
+      } scratch{v.stageJ + tid};
       if (dbg & 2) {   // timing experiment: no algebra
         double z[16] = {x[0][0] + u[1][1] + p[2] + x[3][2] + u[3][0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -571,10 +573,12 @@ __global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
     }
     if (has_inc) {
       if (WANT_J) {
-        const int sw = inc & 3;
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          v.stageJ[(j * CAP + inc) * 4 + (r ^ sw)] = make_double4(blk[4 * r], blk[4 * r + 1], blk[4 * r + 2], blk[4 * r + 3]);
+        {
+          v.stageJ[(j * 8 + 2 * r) * CAP + inc] = make_double2(blk[4 * r], blk[4 * r + 1]);
+          v.stageJ[(j * 8 + 2 * r + 1) * CAP + inc] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
+        }
       }
       if (WANT_F && j == 0) v.stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
     }
