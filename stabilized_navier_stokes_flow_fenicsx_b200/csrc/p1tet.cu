@@ -634,6 +634,7 @@ template <typename K> static cudaError_t smem_attr(K kernel, size_t bytes) {
     if (cap == 256) { OP((k_p1tet_tiles<256, 1, true, true>), (k_p1tet_tiles<256, 1, true, false>), (k_p1tet_tiles<256, 1, false, true>), 256, 256); } \
     else if (cap == 192) { OP((k_p1tet_tiles<192, 1, true, true>), (k_p1tet_tiles<192, 1, true, false>), (k_p1tet_tiles<192, 1, false, true>), 192, 192); } \
     else if (cap == 128) { OP((k_p1tet_tiles<128, 2, true, true>), (k_p1tet_tiles<128, 2, true, false>), (k_p1tet_tiles<128, 2, false, true>), 128, 128); } \
+    else if (cap == 96) { OP((k_p1tet_tiles<96, 3, true, true>), (k_p1tet_tiles<96, 3, true, false>), (k_p1tet_tiles<96, 3, false, true>), 96, 96); } \
     else { OP((k_p1tet_tiles<64, 4, true, true>), (k_p1tet_tiles<64, 4, true, false>), (k_p1tet_tiles<64, 4, false, true>), 64, 64); }             \
   }
 
@@ -839,7 +840,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
                 reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles
   // one-thread kernels are persistent (grid = resident CTAs); the quad kernels take one tile per CTA
-  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 64 ? 4 : 1));
+  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 96 ? 3 : (cap == 64 ? 4 : 1)));
   const unsigned grid = (unsigned)((lanes == 4 || ctx->persistent == 0) ? P->n_tiles : (resident < P->n_tiles ? resident : P->n_tiles));
 #define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
   if (want_J && want_F) KJF<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                        \
