@@ -167,6 +167,8 @@ def run_ours(args):
         asm.set_option("kernel", args.kernel)
     if args.debug:
         asm.set_option("debug", args.debug)
+    if args.ws is not None:
+        asm.set_option("ws", args.ws)
     if args.lanes is not None:
         asm.set_option("lanes", args.lanes)
     if args.threads is not None:
@@ -296,6 +298,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=None, help="0 auto, 1 generic, 2 fast")
     ap.add_argument("--threads", type=int, default=None, help="CTA size of the factorised kernel")
     ap.add_argument("--lanes", type=int, default=None, help="lanes per incidence of the factorised kernel: 1 or 4")
+    ap.add_argument("--ws", type=int, default=None, help="1: warp-specialised variant of the factorised kernel")
     ap.add_argument("--debug", type=int, default=0, help="timing experiments: 1 skip gather phase, 2 skip element algebra")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

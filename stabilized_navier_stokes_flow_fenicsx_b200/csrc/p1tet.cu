@@ -366,24 +366,17 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
       const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
       const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg, const int64_t n_tiles
 
-// one thread per incidence
-template <int CAP, int MINB, bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const TileView<CAP, WANT_J> v(smem_raw);
-  const int tid = threadIdx.x;
-  // persistent CTAs: the grid is a few CTAs per SM, each walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-  // (a fresh CTA per tile costs ~1.4 us of launch/teardown per tile on B200, as much as the tile's own work)
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-  // phase-A inputs are tile-padded: their loads do not depend on the header
-  const int4 vt = inc_vtx[tile * CAP + tid];
-  const int4 ld = inc_lead[tile * CAP + tid];
-  const uint32_t cm = inc_cell[tile * CAP + tid];
-  const TileHdr h = tile_hdr[tile];
-  if (h.nent <= 0) continue;
-  tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+// phase A for one incidence: gather coordinates / state, evaluate the vertex's row slab, Dirichlet handling, park the
+// four blocks (and the residual entries) in the staging area
+#define P1_PHASE_ARGS                                                                                                      \
+  const FormParams &form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,  \
+      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value,                        \
+      const uint8_t *__restrict__ cell_bc, const int dbg
 
-  if (tid < h.ninc) {
+template <int CAP, bool WANT_J, bool WANT_F>
+__device__ __forceinline__ void phase_a(const TileView<CAP, WANT_J>& v, const int tid, const int4 vt, const int4 ld, const uint32_t cm,
+                                        P1_PHASE_ARGS) {
+  {
     const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
     const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
     double x[4][3], u[4][3], p[4];
@@ -487,10 +480,79 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
     }
     if (WANT_F) v.stageF[tid] = make_double4(fr[0], fr[1], fr[2], fr[3]);
   }
-  cp_async_wait_all();
-  __syncthreads();
-  if (!(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
-  __syncthreads();   // staging and tables are reused by the next tile
+}
+
+// one thread per incidence; persistent CTAs (grid = resident CTAs, each walks tiles blockIdx.x, + gridDim.x, ...)
+template <int CAP, int MINB, bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TileView<CAP, WANT_J> v(smem_raw);
+  const int tid = threadIdx.x;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // phase-A inputs are tile-padded: their loads do not depend on the header
+    const int4 vt = inc_vtx[tile * CAP + tid];
+    const int4 ld = inc_lead[tile * CAP + tid];
+    const uint32_t cm = inc_cell[tile * CAP + tid];
+    const TileHdr h = tile_hdr[tile];
+    if (h.nent <= 0) continue;
+    tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+    if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, cell_bc, dbg);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+    __syncthreads();   // staging and tables are reused by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------ warp-specialised variant
+// One persistent CTA per SM, 384 threads: two compute warpgroups (phase A, ~224 registers each) feed one helper warpgroup
+// (gather + stores, 56 registers) through two staging buffers and four named barriers.  The compute warps never wait for
+// the gather and the helper never holds the big register budget, so the three latency chains of a tile (input gathers,
+// element algebra, reduction + stores) overlap instead of adding up.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool WANT_F>
+__global__ void __launch_bounds__(384, 1) k_p1tet_ws(P1_KERNEL_ARGS) {
+  constexpr int CAP = 128;
+  constexpr size_t VIEW = (TileSmem<CAP>::bytes(true) + 48 + 15) & ~(size_t)15;   // + a copy of the tile header
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wg = threadIdx.x >> 7;         // 0, 1: compute warpgroups; 2: helper
+  const int tid = threadIdx.x & 127;
+  const int64_t stride = 2 * (int64_t)gridDim.x;
+  if (wg < 2) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const TileView<CAP, true> v(smem_raw + wg * VIEW);
+    TileHdr* s_hdr = reinterpret_cast<TileHdr*>(smem_raw + wg * VIEW + TileSmem<CAP>::bytes(true));
+    int k = 0;
+    for (int64_t tile = 2 * (int64_t)blockIdx.x + wg; tile < n_tiles; tile += stride, ++k) {
+      const int4 vt = inc_vtx[tile * CAP + tid];
+      const int4 ld = inc_lead[tile * CAP + tid];
+      const uint32_t cm = inc_cell[tile * CAP + tid];
+      const TileHdr h = tile_hdr[tile];
+      if (k > 0) named_bar_sync(3 + wg, 256);            // EMPTY[wg]: the helper is done with the previous tile of this group
+      if (h.nent > 0) tile_tables_async<CAP, CAP, true>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+      if (tid == 0) *s_hdr = h;
+      if (tid < h.ninc) phase_a<CAP, true, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, cell_bc, dbg);
+      cp_async_wait_all();
+      __threadfence_block();
+      named_bar_arrive(1 + wg, 256);                      // FULL[wg]
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    for (int64_t base = 2 * (int64_t)blockIdx.x; base < n_tiles; base += stride) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int64_t tile = base + g;
+        if (tile >= n_tiles) continue;
+        const TileView<CAP, true> v(smem_raw + g * VIEW);
+        const TileHdr* s_hdr = reinterpret_cast<const TileHdr*>(smem_raw + g * VIEW + TileSmem<CAP>::bytes(true));
+        named_bar_sync(1 + g, 256);                       // FULL[g]
+        const TileHdr h = *s_hdr;
+        if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, true, WANT_F>(v, h, tid, vals, F);
+        if (tile + stride < n_tiles) named_bar_arrive(3 + g, 256);   // EMPTY[g] (nobody waits after the group's last tile)
+      }
+    }
   }
 }
 
@@ -836,6 +898,28 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   }
   const uint8_t* cbc = ctx->has_bc ? P->d_cell_bc : nullptr;
   const int lanes = ctx->lanes, cap = P->cap;
+  if (ctx->ws && want_J && lanes == 1 && cap == 128) {
+    // warp-specialised persistent kernel: one CTA per SM
+    constexpr size_t VIEW = (TileSmem<128>::bytes(true) + 48 + 15) & ~(size_t)15;
+    const unsigned grid = (unsigned)(ctx->n_sms < (P->n_tiles + 1) / 2 ? ctx->n_sms : (P->n_tiles + 1) / 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * VIEW)));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * VIEW)));
+      attr_set = true;
+    }
+    if (want_F)
+      k_p1tet_ws<true><<<grid, 384, 2 * VIEW, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc,
+          P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
+          reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
+    else
+      k_p1tet_ws<false><<<grid, 384, 2 * VIEW, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc,
+          P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
+          reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
+    ctx->launches += 1;
+    NS_CUDA(ctx, cudaGetLastError());
+    return NSGPU_OK;
+  }
 #define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
                 reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles

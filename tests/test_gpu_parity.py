@@ -86,8 +86,9 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     asm.close()
 
 
-@pytest.mark.parametrize("kernel,lanes,threads", [(1, 1, 128), (2, 1, 64), (2, 1, 128), (2, 1, 192), (2, 1, 256), (2, 4, 256), (2, 4, 384), (2, 4, 512)])
-def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads):
+@pytest.mark.parametrize("kernel,lanes,threads,ws", [(1, 1, 128, 0), (2, 1, 64, 0), (2, 1, 128, 0), (2, 1, 128, 1), (2, 1, 192, 0), (2, 1, 256, 0),
+                                                      (2, 4, 256, 0), (2, 4, 384, 0), (2, 4, 512, 0)])
+def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads, ws):
     """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernel, which must apply;
     lanes 1: one thread per incidence, lanes 4: four lanes per incidence."""
     m, sp, w, bcs, fk = _case("duct_p1")
@@ -96,6 +97,7 @@ def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads):
     asm = _gpu(m, sp, bcs, fk, kernel)
     asm.set_option("lanes", lanes)
     asm.set_option("threads", threads)
+    asm.set_option("ws", ws)
     asm.create_matrix(fetch=False)
     gv, gF = asm.jacobian_residual(w)
     assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
