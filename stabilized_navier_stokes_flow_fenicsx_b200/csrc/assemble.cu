@@ -7,6 +7,7 @@
 // lifting term, and adds into the CSR values through the precomputed entity-relative position map.
 #include "common.cuh"
 #include "element_p1tet.cuh"
+#include "element_shared.cuh"
 
 namespace nsgpu {
 
@@ -70,6 +71,109 @@ k_assemble_generic(int64_t n_cells, FormParams form, const double* __restrict__ 
   }
 }
 
+// Cooperative variant of the generic path: a CTA takes a batch of cells; the quadrature-point data of each cell
+// (basis tables, fields, stabilisation parameters and their derivatives) is computed once by one thread per (cell, point),
+// parked in shared memory, and consumed by the cell's ND row threads.  On P2-P1 tetrahedra this removes the 34-fold
+// recomputation of the generic kernel.
+template <int GD, int VDEG> struct CoopCfg {
+  static constexpr int ND = ElemTraits<GD, VDEG>::ND;
+  static constexpr int CPB = 256 / ND;                 // cells per block
+  static constexpr int NT = 256;
+};
+
+template <int GD, int VDEG, bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(256)
+k_assemble_coop(int64_t n_cells, FormParams form, const double* __restrict__ xg, const int32_t* __restrict__ cells,
+                const int32_t* __restrict__ dofmap, const double* __restrict__ wv, const uint8_t* __restrict__ bc_marker,
+                const double* __restrict__ bc_value, const int64_t* __restrict__ indptr, const uint16_t* __restrict__ rel,
+                double* __restrict__ vals, double* __restrict__ F) {
+  using T = ElemTraits<GD, VDEG>;
+  constexpr int ND = T::ND, NQ = T::NQ, CPB = CoopCfg<GD, VDEG>::CPB, NT = 256;
+  __shared__ PointData<GD, VDEG> sP[CPB][NQ];
+  __shared__ CellData<GD> sC[CPB];
+  __shared__ double sx[CPB][3 * (GD + 1)];
+  __shared__ double sw[CPB][ND];
+  __shared__ int32_t sdof[CPB][ND];
+  __shared__ uint8_t smk[CPB][ND];
+  __shared__ int sbc[CPB];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = (int64_t)blockIdx.x * CPB;
+  const int ncell = (int)((n_cells - cell0) < CPB ? (n_cells - cell0) : CPB);
+
+  // stage 0: the batch's dofs, coefficients, Dirichlet flags, vertex coordinates
+  if (tid < CPB) sbc[tid] = 0;
+  __syncthreads();
+  for (int t = tid; t < ncell * ND; t += NT) {
+    const int lc = t / ND, k = t - lc * ND;
+    const int32_t d = dofmap[(cell0 + lc) * ND + k];
+    sdof[lc][k] = d;
+    sw[lc][k] = wv[d];
+    const uint8_t mk = bc_marker ? bc_marker[d] : 0;
+    smk[lc][k] = mk;
+    if (mk) sbc[lc] = 1;
+  }
+  for (int t = tid; t < ncell * (GD + 1) * 3; t += NT) {
+    const int lc = t / ((GD + 1) * 3), r = t - lc * (GD + 1) * 3;
+    const int a = r / 3, i = r - 3 * a;
+    sx[lc][r] = xg[3 * (int64_t)cells[(cell0 + lc) * (GD + 1) + a] + i];
+  }
+  __syncthreads();
+  // stage 1: one thread per (cell, quadrature point)
+  for (int t = tid; t < ncell * NQ; t += NT) {
+    const int lc = t / NQ, q = t - lc * NQ;
+    CellData<GD> C;
+    point_setup<GD, VDEG>(form, sx[lc], sw[lc], q, sP[lc][q], C);
+    if (q == 0) sC[lc] = C;
+  }
+  __syncthreads();
+  // stage 2: one thread per (cell, test dof)
+  const int lc = tid / ND, row = tid - lc * ND;
+  if (lc >= ncell) return;
+  const bool cell_bc = sbc[lc] != 0;
+  const bool need_A = WANT_J || (WANT_F && cell_bc);
+  double Arow[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) Arow[k] = 0.0;
+  double b = 0.0;
+  if (need_A) {
+    for (int q = 0; q < NQ; ++q) row_from_point<GD, VDEG, true, WANT_F>(form, sP[lc][q], sC[lc], row, Arow, &b);
+  } else {
+    for (int q = 0; q < NQ; ++q) row_from_point<GD, VDEG, false, WANT_F>(form, sP[lc][q], sC[lc], row, Arow, &b);
+  }
+  const int32_t gi = sdof[lc][row];
+  if (WANT_F) {
+    if (cell_bc) {
+      // apply_lifting(F, [a], [bc], [x], -1.0):  b_e[i] += Ae[i][j] (g_j - x_j) over constrained trial dofs j
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        if (smk[lc][j]) b += Arow[j] * (bc_value[sdof[lc][j]] - sw[lc][j]);
+    }
+    atomicAdd(F + gi, b);
+  }
+  if (WANT_J && !smk[lc][row]) {   // constrained test rows are zeroed: nothing to add
+    const int64_t base = indptr[gi];
+    const uint16_t* r = rel + ((cell0 + lc) * T::NENT + entity_of_local_dof<GD, VDEG>(row)) * ND;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      if (!smk[lc][j]) atomicAdd(vals + base + r[j], Arow[j]);
+  }
+}
+
+template <int GD, int VDEG>
+static void launch_coop(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_F) {
+  constexpr int CPB = CoopCfg<GD, VDEG>::CPB;
+  const unsigned grid = (unsigned)ceil_div(ctx->n_cells_owned > 0 ? ctx->n_cells_owned : 1, CPB);
+  const uint8_t* mk = ctx->has_bc ? ctx->d_bc_marker : nullptr;
+#define NS_LAUNCH(J, F)                                                                                        \
+  k_assemble_coop<GD, VDEG, J, F><<<grid, 256, 0, ctx->stream>>>(ctx->n_cells_owned, ctx->form, ctx->d_x, ctx->d_cells, \
+      ctx->d_dofmap, d_xin, mk, ctx->d_bc_value, ctx->d_indptr, ctx->d_rel, ctx->d_vals, d_F)
+  if (want_J && want_F) NS_LAUNCH(true, true);
+  else if (want_J) NS_LAUNCH(true, false);
+  else NS_LAUNCH(false, true);
+#undef NS_LAUNCH
+  ctx->launches += 1;
+}
+
 // assemble_matrix's diagonal pass: +1.0 per DirichletBC object holding the owned dof
 __global__ void k_bc_diagonal(int64_t n_owned, const int32_t* __restrict__ mult, const int64_t* __restrict__ diag, double* vals) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -122,11 +226,12 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
     if (rc != NSGPU_OK) return rc;
   } else {
     const int key = ctx->gdim * 10 + ctx->vdeg;
+    const bool coop = ctx->kernel_sel != NSGPU_KERNEL_GENERIC;   // AUTO: cooperative (shared point data); GENERIC: thread per row
     switch (key) {
-      case 31: launch_generic<3, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
-      case 32: launch_generic<3, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
-      case 21: launch_generic<2, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
-      case 22: launch_generic<2, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 31: coop ? launch_coop<3, 1>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<3, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 32: coop ? launch_coop<3, 2>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<3, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 21: coop ? launch_coop<2, 1>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<2, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
+      case 22: coop ? launch_coop<2, 2>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<2, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;
       default: set_error(ctx, "unsupported element"); return NSGPU_EUNSUPPORTED;
     }
   }

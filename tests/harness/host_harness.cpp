@@ -84,3 +84,33 @@ extern "C" int harness_p1tet2(double nu, double Ci, const double* x, const doubl
   }
   return 0;
 }
+
+#include "element_shared.cuh"
+
+template <int GD, int VDEG>
+static void run_shared(const FormParams& f, const double* x, const double* w, double* Ae, double* be) {
+  using T = ElemTraits<GD, VDEG>;
+  PointData<GD, VDEG> P[T::NQ];
+  CellData<GD> C;
+  for (int q = 0; q < T::NQ; ++q) point_setup<GD, VDEG>(f, x, w, q, P[q], C);
+  for (int r = 0; r < T::ND; ++r) {
+    double row[T::ND];
+    std::memset(row, 0, sizeof(row));
+    double b = 0.0;
+    for (int q = 0; q < T::NQ; ++q) row_from_point<GD, VDEG, true, true>(f, P[q], C, r, row, &b);
+    for (int j = 0; j < T::ND; ++j) Ae[r * T::ND + j] = row[j];
+    be[r] = b;
+  }
+}
+
+// two-stage (point data shared by the rows of a cell) variant of the generic element tensors
+extern "C" int harness_element_shared(int flavour, int gdim, int vdeg, double nu, double Ci, double alpha, double sp, double beta,
+                                      const double* x, const double* w, double* Ae, double* be) {
+  FormParams f{flavour, nu, Ci, alpha, sp, beta};
+  if (gdim == 3 && vdeg == 1) run_shared<3, 1>(f, x, w, Ae, be);
+  else if (gdim == 3 && vdeg == 2) run_shared<3, 2>(f, x, w, Ae, be);
+  else if (gdim == 2 && vdeg == 1) run_shared<2, 1>(f, x, w, Ae, be);
+  else if (gdim == 2 && vdeg == 2) run_shared<2, 2>(f, x, w, Ae, be);
+  else return -1;
+  return 0;
+}
