@@ -494,6 +494,16 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
     const int4 ld = inc_lead[tile * CAP + tid];
     const uint32_t cm = inc_cell[tile * CAP + tid];
     const TileHdr h = tile_hdr[tile];
+    {  // pull the next tile's streaming inputs into L2 while this one is processed (no registers held)
+      const int64_t nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(inc_vtx + nt * CAP + tid));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(inc_lead + nt * CAP + tid));
+        if ((tid & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(inc_cell + nt * CAP + tid));
+        if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_hdr + nt));
+        if (WANT_J && (tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nt * CAP + tid));
+      }
+    }
     if (h.nent <= 0) continue;
     tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
     if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, cell_bc, dbg);
