@@ -550,6 +550,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
 int p1tet_build_plan(nsgpu_ctx* ctx);
 void p1tet_free(nsgpu_ctx* ctx);
 void p1tet_mark_bc_dirty(nsgpu_ctx* ctx);
+int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y);
 #endif
 
 }  // namespace nsgpu

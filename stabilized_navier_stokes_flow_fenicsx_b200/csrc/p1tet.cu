@@ -47,8 +47,11 @@ struct nsgpu_p1tet_plan {
   TileHdr* d_tile_hdr = nullptr;    // [n_tiles]
   uint8_t* d_tile_bytes = nullptr;  // per tile: slot-list offsets | vertex of each slot | diagonal slot of each vertex (16-B padded segments)
   uint8_t* d_cell_bc = nullptr;     // [n_cells] cell touches a Dirichlet dof
+  int64_t* d_ent_pair0 = nullptr;   // [n_ent] first entry of the vertex's neighbour list in ctx->d_pairs
+  int32_t* d_ent_ns = nullptr;      // [n_ent] number of neighbours (4x4 blocks per row)
   bool contiguous = false;          // every vertex's dofs are (first dof) + 0,1,2,3 and first dof is even
   bool bc_dirty = true;
+  int colx_ok = -1;                 // block SpMV: column ghosts are vertex-contiguous (-1 = not checked yet)
 };
 
 namespace nsgpu {
@@ -69,12 +72,14 @@ struct HiWord {
 __global__ void k_ent_info(int64_t n_ent, const uint32_t* __restrict__ ent_leader, const int32_t* __restrict__ members,
                            const int64_t* __restrict__ pfirst, const int64_t* __restrict__ plast,
                            const uint64_t* __restrict__ pairs, const int64_t* __restrict__ indptr, int64_t* nslots, int64_t* rowpos,
-                           int32_t* rowdof, uint8_t* diag_slot, int* not_contig) {
+                           int32_t* rowdof, uint8_t* diag_slot, int64_t* pair0, int32_t* ns_out, int* not_contig) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e > n_ent) return;
   if (e == n_ent) { nslots[e] = 0; return; }
   const uint32_t A = ent_leader[e];
   nslots[e] = plast[A] - pfirst[A];
+  pair0[e] = pfirst[A];
+  ns_out[e] = (int32_t)(plast[A] - pfirst[A]);
   {  // slot of the vertex in its own neighbour list (the diagonal block)
     int64_t lo = pfirst[A], hi = plast[A] - 1, found = 0;
     while (lo <= hi) {
@@ -660,12 +665,73 @@ __global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
   tile_gather<CAP, NT, WANT_J, WANT_F>(v, h, tid, vals, F);
 }
 
+static inline unsigned g256(int64_t n);
+// ------------------------------------------------------------------------------------------ block SpMV
+// MatMult for the vertex-blocked P1-P1 matrix: the CSR values are walked as 4x4 blocks (vertex A, neighbour B) with ONE
+// column index per block, taken from the entity pair list of the pattern build, instead of 16 int32 column indices.
+// Sixteen lanes per vertex; lane s owns neighbour s: one 32-byte load of x[B], four 32-byte loads of values (one per row,
+// contiguous across lanes), 16 FMAs; the four row sums are reduced over the lanes with shuffles.
+__global__ void __launch_bounds__(256)
+k_spmv_block4(int64_t n_ent, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
+              const uint64_t* __restrict__ pairs, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
+              const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t >> 4;
+  const int lane = (int)(t & 15);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int4 rd = make_int4(0, 0, 0, 0);
+  if (e < n_ent) {
+    rd = rowdof[e];
+    if (rd.x < n_owned) {
+      const int n = ns[e];
+      const int64_t p0 = pair0[e];
+      const longlong2* rp = reinterpret_cast<const longlong2*>(rowpos + 4 * e);
+      const longlong2 r01 = rp[0], r23 = rp[1];
+      const int64_t rpos[4] = {r01.x, r01.y, r23.x, r23.y};
+      for (int s = lane; s < n; s += 16) {
+        const uint32_t B = (uint32_t)(pairs[p0 + s] & 0xffffffffu);
+        const double2* xp = reinterpret_cast<const double2*>(x + B);
+        const double2 xa = __ldg(xp), xb = __ldg(xp + 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double2* vp = reinterpret_cast<const double2*>(vals + rpos[c] + 4 * s);
+          const double2 va = __ldcs(vp), vb = __ldcs(vp + 1);
+          acc[c] += va.x * xa.x + va.y * xa.y + vb.x * xb.x + vb.y * xb.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o, 16);
+  }
+  if (e < n_ent && lane == 0 && rd.x < n_owned) {
+    y[rd.x] = acc[0]; y[rd.y] = acc[1]; y[rd.z] = acc[2]; y[rd.w] = acc[3];
+  }
+}
+
+// returns 1 when the block kernel ran, 0 when the caller should use the plain CSR kernel
+int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  if (!P || !P->contiguous || !ctx->d_pairs || P->n_ent == 0) return 0;
+  if (P->colx_ok < 0) {   // column ghosts received from other ranks must be vertex-contiguous too (leader + 0..3, 32-byte aligned)
+    P->colx_ok = (ctx->n_dofs % 4 == 0) ? 1 : 0;
+    for (size_t k = 0; k < ctx->colx_leader.size() && P->colx_ok; ++k)
+      if (ctx->colx_leader[k] + ctx->colx_slot[k] != (int64_t)ctx->n_dofs + (int64_t)k || ctx->colx_size[k] != 4 || ctx->colx_leader[k] % 4 != 0) P->colx_ok = 0;
+  }
+  if (!P->colx_ok) return 0;
+  k_spmv_block4<<<g256(P->n_ent * 16), 256, 0, ctx->stream>>>(P->n_ent, ctx->n_owned, P->d_ent_pair0, P->d_ent_ns, ctx->d_pairs, P->d_rowpos,
+                                                            reinterpret_cast<const int4*>(P->d_rowdof), ctx->d_vals, d_x, d_y);
+  return 1;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) return;
   cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
-  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_cell_bc);
+  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_cell_bc); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
   delete P;
   ctx->p1plan = nullptr;
 }
@@ -809,8 +875,10 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_CUDA(cudaMalloc(&d_diag, n_ent + 1));
   PL_CUDA(cudaMalloc(&P->d_rowpos, sizeof(int64_t) * n_ent * 4));
   PL_CUDA(cudaMalloc(&P->d_rowdof, sizeof(int32_t) * n_ent * 4));
+  PL_CUDA(cudaMalloc(&P->d_ent_pair0, sizeof(int64_t) * (n_ent + 1)));
+  PL_CUDA(cudaMalloc(&P->d_ent_ns, sizeof(int32_t) * (n_ent + 1)));
   k_ent_info<<<g256(n_ent + 1), 256, 0, s>>>(n_ent, d_leader, ctx->d_members, ctx->d_pair_first, ctx->d_pair_last, ctx->d_pairs,
-                                             ctx->d_indptr, d_nslots, P->d_rowpos, P->d_rowdof, d_diag, d_flag + 1);
+                                             ctx->d_indptr, d_nslots, P->d_rowpos, P->d_rowdof, d_diag, P->d_ent_pair0, P->d_ent_ns, d_flag + 1);
   PL_SCAN(d_nslots, d_slot_ptr, n_ent + 1);
   int64_t n_slots = 0;
   PL_CUDA(cudaMemcpy(&n_slots, d_slot_ptr + n_ent, sizeof(int64_t), cudaMemcpyDeviceToHost));

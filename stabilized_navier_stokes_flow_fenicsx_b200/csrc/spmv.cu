@@ -3,6 +3,7 @@
 // P2-P1 ~100-400: a sub-warp of LPR lanes walks one row with coalesced value/column loads and gathers x
 // through the read-only path; partial sums are combined with shuffles.
 #include "common.cuh"
+#include "element_p1tet.cuh"
 
 namespace nsgpu {
 
@@ -29,6 +30,9 @@ int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
   const int bs = 256;
   cudaStream_t s = ctx->stream;
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+  if (ctx->kernel_sel != NSGPU_KERNEL_GENERIC && p1tet_spmv(ctx, d_x, d_y)) {
+    // vertex-blocked P1-P1 matrix: one column index per 4x4 block (p1tet.cu)
+  } else
   if (avg > 48) k_spmv<16><<<(unsigned)ceil_div(n * 16, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
   else if (avg > 24) k_spmv<8><<<(unsigned)ceil_div(n * 8, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
   else k_spmv<4><<<(unsigned)ceil_div(n * 4, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
