@@ -269,6 +269,9 @@ def run_ours(args):
                          "traffic_source": (NCU_TRAFFIC[args.workload][1] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
                          "peak_source": how, "kernel_ms": kernel_ms_avg, "algorithmic_bytes": b_jf,
                          "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): ncu shows DRAM ~5 %, fp64 pipe ~25 % busy"},
+            "fp64": {"flop_per_cell_executed": 5600, "achieved_TFLOP/s": 5600 * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
+                     "peak_TFLOP/s": 33.9 * world, "frac": 5600 * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (33.9 * world),
+                     "source": "executed DFMA/DMUL/DADD counts from ncu (profiles/r1_ncu_full_L_p1tet_v5_and_spmv.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
             "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
                               "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
             "spmv": {"ms": s_ms, "GB/s": b_spmv / (s_ms * 1e-3) / 1e9, "frac": b_spmv / (s_ms * 1e-3) / 1e9 / hbm_total,
