@@ -90,6 +90,7 @@ struct nsgpu_ctx {
   int kernel_sel = NSGPU_KERNEL_AUTO;
   int n_sms = 148;     // SM count of the device (nsgpu_create)
   int ws = 0;          // row-owner kernel: warp-specialised variant (compute warpgroups + helper warpgroup)
+  int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
   int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)
   int debug = 0;       // timing experiments only (bit 0: skip the gather phase, bit 1: skip the element algebra)
   int lanes = 1;       // lanes per incidence in the row-owner kernel: 1 (p1tet_rowslab) or 4 (p1tet_quad)

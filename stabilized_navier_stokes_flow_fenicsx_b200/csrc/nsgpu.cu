@@ -432,11 +432,13 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: kernel must be 0 (auto), 1 (generic) or 2 (fast)");
     ctx->kernel_sel = (int)value;
   } else if (!strcmp(name, "threads")) {
-    NS_REQUIRE(ctx, value == 64 || value == 96 || value == 128 || value == 192 || value == 256 || value == 384 || value == 512,
-               "set_option: threads must be 64, 96, 128, 192, 256, 384 or 512");
+    NS_REQUIRE(ctx, value == 32 || value == 64 || value == 96 || value == 128 || value == 192 || value == 256 || value == 384 || value == 512,
+               "set_option: threads must be 32, 64, 96, 128, 192, 256, 384 or 512");
     ctx->threads = (int)value;
   } else if (!strcmp(name, "ws")) {
     ctx->ws = value != 0;
+  } else if (!strcmp(name, "pipe")) {
+    ctx->pipe = value != 0;
   } else if (!strcmp(name, "persistent")) {
     ctx->persistent = value != 0;
   } else if (!strcmp(name, "debug")) {

@@ -20,24 +20,33 @@
 //
 // The plan (incidence lists, tiles, gather lists, output positions) is built once per pattern, on the
 // device, from the entity-level pair list the pattern builder already sorted.
+#include <cstdio>
+#include <vector>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
 #include "element_p1tet.cuh"
 
+constexpr int TILE_MAX_ENT = 40;
+constexpr int PIPE_VCAP = 128;     // distinct vertices per tile the pipelined kernel stages (plan->max_nv must not exceed it)   // most vertices in one tile (tile formation in p1tet_build_plan)
+
 struct TileHdr {
   int64_t e0;      // first vertex (entity) of the tile
   int64_t boff;    // offset of the tile's byte tables in d_tile_bytes (16-byte aligned)
-  int nent, ninc, nslots, pad;
+  int nent, ninc, nslots, nv;   // nv: distinct mesh vertices the tile's incidences touch (k_tile_vlist)
 };
 
 struct nsgpu_p1tet_plan {
   int64_t n_inc = 0, n_ent = 0, n_tiles = 0, n_slots = 0;
-  int cap = 0, maxdeg = 0;
+  int cap = 0, maxdeg = 0, max_nent = 0;   // max_nent: most vertices in one tile
   // per incidence, TILE-PADDED: entry k of tile t lives at t * cap + k (so phase-A loads do not wait for the header)
-  uint32_t* d_inc_cell = nullptr;   // cell * 4 + local vertex
+  uint32_t* d_inc_cell = nullptr;   // cell * 4 + local vertex; bit 31: the cell touches a Dirichlet dof (refreshed when the BCs change)
   int4* d_inc_vtx = nullptr;        // geometry vertex ids, row vertex first (rotated order)
   int4* d_inc_lead = nullptr;       // first dof of the 4 vertices, same order
+  int2* d_tile_vlist = nullptr;     // [n_tiles][PIPE_VCAP] distinct vertices of the tile: (geometry vertex, first dof)
+  uint32_t* d_inc_loc = nullptr;    // [n_tiles * cap] the incidence's four vertices as positions in that list (one byte each, row vertex first)
+  int max_nv = 0;                   // most distinct vertices in one tile
   uint32_t* d_src = nullptr;        // gather lists, 4 bytes per incidence: (incidence-within-vertex << 2 | block), grouped by slot
   // per vertex (entity), compact
   int2* d_ent_rel = nullptr;        // (incidence offset, slot offset) relative to the tile start
@@ -46,7 +55,6 @@ struct nsgpu_p1tet_plan {
   // per tile
   TileHdr* d_tile_hdr = nullptr;    // [n_tiles]
   uint8_t* d_tile_bytes = nullptr;  // per tile: slot-list offsets | vertex of each slot | diagonal slot of each vertex (16-B padded segments)
-  uint8_t* d_cell_bc = nullptr;     // [n_cells] cell touches a Dirichlet dof
   int64_t* d_ent_pair0 = nullptr;   // [n_ent] first entry of the vertex's neighbour list in ctx->d_pairs
   int32_t* d_ent_ns = nullptr;      // [n_ent] number of neighbours (4x4 blocks per row)
   bool contiguous = false;          // every vertex's dofs are (first dof) + 0,1,2,3 and first dof is even
@@ -162,27 +170,17 @@ __global__ void k_slot_start(int64_t n_ent, const int64_t* __restrict__ slot_ptr
   if (run > 252) *bad = 1;
 }
 
-__global__ void k_tiles(int64_t n_tiles, int64_t n_ent, int64_t capeff, const int64_t* __restrict__ inc_ptr, int64_t* tile_ent) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t > n_tiles) return;
-  const int64_t target = t * capeff;   // first entity whose incidence offset is >= target
-  int64_t lo = 0, hi = n_ent;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (inc_ptr[mid] < target) lo = mid + 1; else hi = mid;
-  }
-  tile_ent[t] = lo;
-}
-
 __host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
 
-__global__ void k_tile_sizes(int64_t n_tiles, const int64_t* __restrict__ tile_ent, const int64_t* __restrict__ slot_ptr, int64_t* sizes) {
+__global__ void k_tile_sizes(int64_t n_tiles, const int64_t* __restrict__ tile_ent, const int64_t* __restrict__ slot_ptr, int64_t* sizes,
+                             int* max_nent) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   if (t == n_tiles) { sizes[t] = 0; return; }
   const int64_t e0 = tile_ent[t], e1 = tile_ent[t + 1];
   const int nent = (int)(e1 - e0), nslots = (int)(slot_ptr[e1] - slot_ptr[e0]);
   sizes[t] = pad16(nslots + nent + 1) + pad16(nslots) + pad16(nent);
+  atomicMax(max_nent, nent);
 }
 
 // one CTA per tile: header, tile-relative vertex offsets, tile-padded incidence arrays, byte tables
@@ -197,7 +195,7 @@ __global__ void k_tile_pack(int cap, const int64_t* __restrict__ tile_ent, const
   const int nent = (int)(e1 - e0), ninc = (int)(inc_ptr[e1] - i0), nslots = (int)(slot_ptr[e1] - s0);
   if (threadIdx.x == 0) {
     TileHdr h;
-    h.e0 = e0; h.boff = boff[t]; h.nent = nent; h.ninc = ninc; h.nslots = nslots; h.pad = 0;
+    h.e0 = e0; h.boff = boff[t]; h.nent = nent; h.ninc = ninc; h.nslots = nslots; h.nv = 0;
     hdr[t] = h;
   }
   for (int k = threadIdx.x; k < cap; k += blockDim.x) {
@@ -219,49 +217,114 @@ __global__ void k_tile_pack(int cap, const int64_t* __restrict__ tile_ent, const
   }
 }
 
-__global__ void k_cell_bc(int64_t n_cells, const int32_t* __restrict__ dofmap, const uint8_t* __restrict__ marker, uint8_t* cell_bc) {
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= n_cells) return;
+// per tile (CAP = 128 incidences): the DISTINCT mesh vertices its incidences touch (~40 instead of 4 x 128), and each incidence's
+// four vertices as byte positions in that list.  The pipelined kernel stages coordinates and state once per distinct vertex.
+__global__ void __launch_bounds__(128) k_tile_vlist(TileHdr* __restrict__ hdr, const int4* __restrict__ p_vtx, const int4* __restrict__ p_lead,
+                                                    int2* __restrict__ vlist, uint32_t* __restrict__ inc_loc, int* max_nv) {
+  using Sort = cub::BlockRadixSort<uint32_t, 128, 4>;
+  using Scan = cub::BlockScan<int, 128>;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  __shared__ uint32_t sorted[512], uniq[512];
+  const int64_t t = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ninc = hdr[t].ninc;
+  const int4 vt = p_vtx[t * 128 + tid], ld = p_lead[t * 128 + tid];
+  const uint32_t vtx[4] = {(uint32_t)vt.x, (uint32_t)vt.y, (uint32_t)vt.z, (uint32_t)vt.w};
+  const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
+  uint32_t keys[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) keys[a] = tid < ninc ? vtx[a] : 0xffffffffu;
+  Sort(tmp.sort).Sort(keys);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sorted[4 * tid + k] = keys[k];
+  __syncthreads();
+  int flags[4], pos[4], total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 4 * tid + k;
+    flags[k] = (keys[k] != 0xffffffffu && (i == 0 || sorted[i - 1] != keys[k])) ? 1 : 0;
+  }
+  Scan(tmp.scan).ExclusiveSum(flags, pos, total);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (flags[k]) uniq[pos[k]] = keys[k];
+  __syncthreads();
+  uint32_t packed = 0;
+  if (tid < ninc) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int lo = 0, hi = total - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (uniq[mid] < vtx[a]) lo = mid + 1; else hi = mid;
+      }
+      if (lo < PIPE_VCAP) vlist[t * PIPE_VCAP + lo] = make_int2((int)vtx[a], lead[a]);   // same value from every incidence that touches it
+      packed |= (uint32_t)(lo & 255) << (8 * a);
+    }
+  }
+  inc_loc[t * 128 + tid] = packed;
+  if (tid == 0) { hdr[t].nv = total; atomicMax(max_nv, total); }
+}
+
+// per (tile-padded) incidence: does its cell touch a Dirichlet dof?  The flag rides in bit 31 of the incidence's cell word,
+// so the kernels get it with the tile's index loads instead of through a dependent per-cell lookup.
+constexpr uint32_t INC_BC_BIT = 0x80000000u;
+__global__ void k_inc_bc(int64_t n, uint32_t* __restrict__ inc_cell, const int32_t* __restrict__ dofmap, const uint8_t* __restrict__ marker) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t cm = inc_cell[i] & ~INC_BC_BIT;
+  const int64_t c = cm >> 2;
   uint8_t f = 0;
-  for (int k = 0; k < 16; ++k) f |= marker[dofmap[c * 16 + k]];
-  cell_bc[c] = f;
+  if (marker)
+    for (int k = 0; k < 16; ++k) f |= marker[dofmap[c * 16 + k]];
+  inc_cell[i] = cm | (f ? INC_BC_BIT : 0u);
 }
 
 // ------------------------------------------------------------------------------------------ the kernels
-template <int CAP> struct TileSmem {
+template <int CAP, int ECAP = CAP> struct TileSmem {
   // stageJ [4 blocks][8 pieces][CAP] double2 (piece k = 2 * row + half; incidence-minor: conflict-free writes) | stageF [CAP] double4 |
-  // rowpos [CAP][4] i64 | rowdof [CAP] int4 | rel [CAP+2] int2 | src [CAP] u32 | byte tables
+  // rowpos [ECAP][4] i64 | rowdof [ECAP] int4 | rel [ECAP+2] int2 | src [CAP] u32 | byte tables
+  // ECAP = vertices per tile the tables have room for (CAP is always enough; the ring kernel trims it to fit three buffers)
   static constexpr int kBytes = ((5 * CAP + 1 + 15) & ~15) + ((4 * CAP + 15) & ~15) + ((CAP + 15) & ~15);
   static constexpr size_t stageJ = 16 * (size_t)CAP * sizeof(double4);
   static constexpr size_t stageF = (size_t)CAP * sizeof(double4);
-  static constexpr size_t tables = 32 * CAP + 16 * CAP + 8 * (CAP + 2) + 4 * CAP + kBytes;
+  static constexpr size_t tables = 32 * ECAP + 16 * ECAP + 8 * (ECAP + 2) + 4 * CAP + kBytes;
   static constexpr size_t bytes(bool want_J) { return (want_J ? stageJ : 0) + stageF + tables; }
 };
 
-template <int CAP, bool WANT_J> struct TileView {
+template <int CAP_, bool WANT_J, int ECAP = CAP_> struct TileView {
+  static constexpr int CAP = CAP_;
   double2* stageJ; double4* stageF; int64_t* rowpos; int4* rowdof; int2* rel; uint32_t* src; uint8_t* bytes;
   __device__ explicit TileView(unsigned char* raw) {
     stageJ = reinterpret_cast<double2*>(raw);
     stageF = reinterpret_cast<double4*>(stageJ + (WANT_J ? 32 * CAP : 0));
     rowpos = reinterpret_cast<int64_t*>(stageF + CAP);
-    rowdof = reinterpret_cast<int4*>(rowpos + 4 * CAP);
-    rel = reinterpret_cast<int2*>(rowdof + CAP);
-    src = reinterpret_cast<uint32_t*>(rel + (CAP + 2));
+    rowdof = reinterpret_cast<int4*>(rowpos + 4 * ECAP);
+    rel = reinterpret_cast<int2*>(rowdof + ECAP);
+    src = reinterpret_cast<uint32_t*>(rel + (ECAP + 2));
     bytes = reinterpret_cast<uint8_t*>(src + CAP);
   }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // asynchronous global -> shared copy of the tile's tables (no registers held; completes behind phase A)
-template <int CAP, int NT, bool WANT_J>
-__device__ __forceinline__ void tile_tables_async(const TileView<CAP, WANT_J>& v, const TileHdr& h, int tid, int64_t tile,
+template <int CAP, int NT, bool WANT_J, class View>
+__device__ __forceinline__ void tile_tables_async(const View& v, const TileHdr& h, int tid, int64_t tile,
                                                   const uint32_t* __restrict__ src, const uint8_t* __restrict__ tile_bytes,
                                                   const int2* __restrict__ ent_rel, const int64_t* __restrict__ rowpos,
                                                   const int4* __restrict__ rowdof) {
@@ -287,9 +350,13 @@ __device__ __forceinline__ double quad_sum_b(double v) {
   return v;
 }
 
+// staging layout: piece k (= 2 * row + half, one double2) of block n of incidence i; incidence-minor, so a warp's phase-A
+// stores and its own-slot reloads are conflict-free
+__device__ __forceinline__ int stage_idx(const int CAP, const int n, const int k, const int i) { return (n * 8 + k) * CAP + i; }
+
 // phase B: gather the parked row slabs into finished CSR row pieces (and residual entries)
-template <int CAP, int NT, bool WANT_J, bool WANT_F>
-__device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, const TileHdr& h, int tid, double* __restrict__ vals,
+template <int CAP, int NT, bool WANT_J, bool WANT_F, class View>
+__device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int tid, double* __restrict__ vals,
                                             double* __restrict__ F) {
   const uint8_t* s_ss = v.bytes;
   const uint8_t* eos = v.bytes + pad16(h.nslots + h.nent + 1);
@@ -366,7 +433,7 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
 #define P1_KERNEL_ARGS                                                                                                     \
   FormParams form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,          \
       const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value,                        \
-      const uint8_t *__restrict__ cell_bc, const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,              \
+      const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,                                                  \
       const int4 *__restrict__ inc_lead, const uint32_t *__restrict__ src, const uint8_t *__restrict__ tile_bytes,               \
       const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
       const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg, const int64_t n_tiles
@@ -375,57 +442,29 @@ __device__ __forceinline__ void tile_gather(const TileView<CAP, WANT_J>& v, cons
 // four blocks (and the residual entries) in the staging area
 #define P1_PHASE_ARGS                                                                                                      \
   const FormParams &form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,  \
-      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value,                        \
-      const uint8_t *__restrict__ cell_bc, const int dbg
+      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value, const int dbg
 
-template <int CAP, bool WANT_J, bool WANT_F>
-__device__ __forceinline__ void phase_a(const TileView<CAP, WANT_J>& v, const int tid, const int4 vt, const int4 ld, const uint32_t cm,
-                                        P1_PHASE_ARGS) {
+template <int CAP, bool WANT_J, bool WANT_F, class View>
+__device__ __forceinline__ void phase_a_core(const View& v, const int tid, const int (&lead)[4], const uint32_t cm, const double (&x)[4][3],
+                                             const double (&u)[4][3], const double (&p)[4], P1_PHASE_ARGS) {
   {
-    const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
-    const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
-    double x[4][3], u[4][3], p[4];
-    int dof[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double* xp = xg + 3 * (int64_t)vtx[a];
-      if (dbg & 4) {
-        x[a][0] = vtx[a]; x[a][1] = a; x[a][2] = lead[a]; u[a][0] = 1; u[a][1] = 2; u[a][2] = 3; p[a] = 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dof[a][c] = lead[a] + c;
-        continue;
-      }
-      x[a][0] = xp[0]; x[a][1] = xp[1]; x[a][2] = xp[2];
-      if (contiguous) {
-        const double2* wp = reinterpret_cast<const double2*>(wv + lead[a]);
-        const double2 w01 = wp[0], w23 = wp[1];
-        u[a][0] = w01.x; u[a][1] = w01.y; u[a][2] = w23.x; p[a] = w23.y;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dof[a][c] = lead[a] + c;
-      } else {
-        const int4 mem = reinterpret_cast<const int4*>(members)[lead[a]];
-        dof[a][0] = mem.x; dof[a][1] = mem.y; dof[a][2] = mem.z; dof[a][3] = mem.w;
-        u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
-      }
-    }
+    const bool has_bc = (cm & INC_BC_BIT) != 0;
     double fr[4] = {0.0, 0.0, 0.0, 0.0};
     const bool row_is_origin = (cm & 3u) == 0;
-    const bool has_bc = cell_bc && cell_bc[cm >> 2];
     bool rowbc[4] = {false, false, false, false};
     if (has_bc) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) rowbc[r] = bc_marker[dof[0][r]] != 0;
+      for (int r = 0; r < 4; ++r) rowbc[r] = bc_marker[contiguous ? lead[0] + r : members[(int64_t)lead[0] * KMAX + r]] != 0;
     }
-    const int sw = tid & 3;
     // finished block n: Dirichlet handling at element level (assemble_matrix / apply_lifting semantics),
     // then straight into the thread's staging slot
     auto emit = [&](const int n, double (&blk)[16]) {
       if (has_bc) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          const int32_t dj = dof[n][d];
+          const int32_t dj = contiguous ? lead[n] + d : members[(int64_t)lead[n] * KMAX + d];   // rare path: re-derived, not kept live
           if (bc_marker[dj]) {
-            const double delta = bc_value[dj] - ((d < 3) ? u[n][d] : p[n]);
+            const double delta = bc_value[dj] - wv[dj];   // re-read (rare path) instead of keeping the nodal state live
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               if (WANT_F) fr[r] += blk[4 * r + d] * delta;   // lifting with the un-zeroed entry
@@ -444,28 +483,28 @@ __device__ __forceinline__ void phase_a(const TileView<CAP, WANT_J>& v, const in
 #pragma unroll
         for (int r = 0; r < 4; ++r)
         {
-          v.stageJ[(n * 8 + 2 * r) * CAP + tid] = make_double2(blk[4 * r], blk[4 * r + 1]);
-          v.stageJ[(n * 8 + 2 * r + 1) * CAP + tid] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
+          v.stageJ[stage_idx(CAP, n, 2 * r, tid)] = make_double2(blk[4 * r], blk[4 * r + 1]);
+          v.stageJ[stage_idx(CAP, n, 2 * r + 1, tid)] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
         }
       }
     };
     if (WANT_J) {
       // point data of q = 1..3 waits in the (not yet written) staging slot of block q
       struct SmemScratch {
-        double2* base;   // this thread's column of the staging area: piece (q, k) at base[(q * 8 + k) * CAP]
+        double2* st;   // staging area; the five pieces of point q wait in pieces 0..4 of the thread's (not yet written) block q
+        int tid;
         __device__ void put(int q, const P1TetPoint& pt) const {
-          double2* s = base + q * 8 * CAP;
-          s[0] = make_double2(pt.uq[0], pt.uq[1]); s[CAP] = make_double2(pt.uq[2], pt.Gu[0]);
-          s[2 * CAP] = make_double2(pt.Gu[1], pt.Gu[2]); s[3 * CAP] = make_double2(pt.ew, pt.eb);
-          s[4 * CAP] = make_double2(pt.ea, 0.0);
+          st[stage_idx(CAP, q, 0, tid)] = make_double2(pt.uq[0], pt.uq[1]); st[stage_idx(CAP, q, 1, tid)] = make_double2(pt.uq[2], pt.Gu[0]);
+          st[stage_idx(CAP, q, 2, tid)] = make_double2(pt.Gu[1], pt.Gu[2]); st[stage_idx(CAP, q, 3, tid)] = make_double2(pt.ew, pt.eb);
+          st[stage_idx(CAP, q, 4, tid)] = make_double2(pt.ea, 0.0);
         }
         __device__ void get(int q, P1TetPoint& pt) const {
-          const double2* s = base + q * 8 * CAP;
-          const double2 a = s[0], b = s[CAP], c = s[2 * CAP], d = s[3 * CAP], e = s[4 * CAP];
+          const double2 a = st[stage_idx(CAP, q, 0, tid)], b = st[stage_idx(CAP, q, 1, tid)], c = st[stage_idx(CAP, q, 2, tid)],
+                        d = st[stage_idx(CAP, q, 3, tid)], e = st[stage_idx(CAP, q, 4, tid)];
           pt.uq[0] = a.x; pt.uq[1] = a.y; pt.uq[2] = b.x; pt.Gu[0] = b.y;
           pt.Gu[1] = c.x; pt.Gu[2] = c.y; pt.ew = d.x; pt.eb = d.y; pt.ea = e.x;
         }
-      } scratch{v.stageJ + tid};
+      } scratch{v.stageJ, tid};
       if (dbg & 2) {   // timing experiment: no algebra
         double z[16] = {x[0][0] + u[1][1] + p[2] + x[3][2] + u[3][0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -485,6 +524,28 @@ __device__ __forceinline__ void phase_a(const TileView<CAP, WANT_J>& v, const in
     }
     if (WANT_F) v.stageF[tid] = make_double4(fr[0], fr[1], fr[2], fr[3]);
   }
+}
+
+// phase A with the inputs gathered straight from global memory (coordinates by vertex id, state by first dof)
+template <int CAP, bool WANT_J, bool WANT_F, class View>
+__device__ __forceinline__ void phase_a(const View& v, const int tid, const int4 vt, const int4 ld, const uint32_t cm, P1_PHASE_ARGS) {
+  const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
+  const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
+  double x[4][3], u[4][3], p[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double* xp = xg + 3 * (int64_t)vtx[a];
+    x[a][0] = xp[0]; x[a][1] = xp[1]; x[a][2] = xp[2];
+    if (contiguous) {
+      const double2* wp = reinterpret_cast<const double2*>(wv + lead[a]);
+      const double2 w01 = wp[0], w23 = wp[1];
+      u[a][0] = w01.x; u[a][1] = w01.y; u[a][2] = w23.x; p[a] = w23.y;
+    } else {
+      const int4 mem = reinterpret_cast<const int4*>(members)[lead[a]];
+      u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
+    }
+  }
+  phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
 }
 
 // one thread per incidence; persistent CTAs (grid = resident CTAs, each walks tiles blockIdx.x, + gridDim.x, ...)
@@ -511,7 +572,7 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
     }
     if (h.nent <= 0) continue;
     tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
-    if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, cell_bc, dbg);
+    if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
     cp_async_wait_all();
     __syncthreads();
     if (!(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
@@ -519,54 +580,181 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
   }
 }
 
-// ------------------------------------------------------------------------------------------ warp-specialised variant
-// One persistent CTA per SM, 384 threads: two compute warpgroups (phase A, ~224 registers each) feed one helper warpgroup
-// (gather + stores, 56 registers) through two staging buffers and four named barriers.  The compute warps never wait for
-// the gather and the helper never holds the big register budget, so the three latency chains of a tile (input gathers,
-// element algebra, reduction + stores) overlap instead of adding up.
+// ------------------------------------------------------------------------------------------ software-pipelined variant
+// Same tile algorithm as k_p1tet_tiles (128 incidences, 2 CTAs/SM), but no thread ever waits for DRAM and the inputs are
+// fetched ONCE PER DISTINCT VERTEX of the tile (~40) instead of once per (incidence, vertex) (512): the unpipelined kernel
+// issues 20 scattered loads per thread, which keeps the L1 tag stage busy for ~2500 cycles per tile, and the ncu profile
+// attributed ~22 % of the warp time to waiting for them plus ~14 % to the barrier behind them
+// (profiles/r1_ncu_full_L_p1tet_v5_and_spmv.txt).  Everything arrives in shared memory through cp.async, issued one or two
+// tiles ahead:
+//   iteration j of a persistent CTA (tiles t_j = blockIdx.x + j * gridDim.x):
+//     LDS own vertex positions / cell word (index ring slot j % 3), then own inputs from the vertex table (buffer j & 1)
+//     cp.async tables(j)                       [group A]  gather lists / row positions of this tile (needed after the algebra)
+//     cp.async vertex table(j+1)               [group B]  cooperative: 5 copies (3 x 8 B coordinates, 2 x 16 B state) per distinct vertex
+//     cp.async index ring(j+2), header(j+2)    [group B]
+//     element algebra (registers only), park the row slab
+//     wait_group 1 (= tables), barrier, gather + stores, wait_group 0, barrier (which also publishes table(j+1) / ring(j+2))
+// Requires vertex-contiguous dofs, <= PIPE_ECAP vertices and <= PIPE_VCAP distinct mesh vertices per tile.
+constexpr int PIPE_ECAP = TILE_MAX_ENT;
+constexpr int PIPE_VREC = 5;   // double2 per vertex record: (x0 x1)(x2 -)(u0 u1)(u2 p)(pad): 80-byte stride keeps 8 consecutive records on distinct banks
+template <bool WANT_J> struct PipeSmem {
+  static constexpr int CAP = 128;
+  static constexpr size_t view = TileSmem<CAP, PIPE_ECAP>::bytes(WANT_J);
+  static constexpr size_t table = (size_t)PIPE_VCAP * PIPE_VREC * sizeof(double2);
+  static constexpr size_t ring = PIPE_VCAP * sizeof(int2) + 2 * CAP * sizeof(uint32_t);
+  static constexpr size_t bytes = view + 2 * table + 3 * ring + 3 * sizeof(TileHdr);
+};
+
+template <bool WANT_J, bool WANT_F>
+__global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int2* __restrict__ tile_vlist, const uint32_t* __restrict__ inc_loc) {
+  constexpr int CAP = 128;
+  using View = TileView<CAP, WANT_J, PIPE_ECAP>;
+  using PS = PipeSmem<WANT_J>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const View v(smem_raw);
+  double2* tab = reinterpret_cast<double2*>(smem_raw + PS::view);                   // [2][PIPE_VCAP][PIPE_VREC]
+  unsigned char* ring = smem_raw + PS::view + 2 * PS::table;                          // [3] { int2 vl[PIPE_VCAP]; u32 loc[CAP]; u32 cm[CAP]; }
+  TileHdr* r_hdr = reinterpret_cast<TileHdr*>(ring + 3 * PS::ring);                   // [3]
+  const int tid = threadIdx.x;
+  const int64_t nj = (n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto r_vl = [&](int s) { return reinterpret_cast<int2*>(ring + s * PS::ring); };
+  auto r_loc = [&](int s) { return reinterpret_cast<uint32_t*>(ring + s * PS::ring + PIPE_VCAP * sizeof(int2)); };
+  auto r_cm = [&](int s) { return r_loc(s) + CAP; };
+  auto fetch_idx = [&](const int64_t j) {
+    const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
+    const int s = (int)(j % 3);
+    cp_async8(r_vl(s) + tid, tile_vlist + t * PIPE_VCAP + tid);
+    cp_async4(r_loc(s) + tid, inc_loc + t * CAP + tid);
+    cp_async4(r_cm(s) + tid, inc_cell + t * CAP + tid);
+    if (tid < 2) cp_async16(reinterpret_cast<unsigned char*>(r_hdr + s) + 16 * tid, reinterpret_cast<const unsigned char*>(tile_hdr + t) + 16 * tid);
+  };
+  auto fetch_inputs = [&](const int64_t j) {   // the header and vertex list of tile j are already visible in their ring slots
+    const int s = (int)(j % 3);
+    const int n = r_hdr[s].nv * PIPE_VREC;
+    double2* dst = tab + (j & 1) * (PIPE_VCAP * PIPE_VREC);
+    const int2* vl = r_vl(s);
+    for (int item = tid; item < n; item += CAP) {
+      const int i = item / PIPE_VREC, c = item - i * PIPE_VREC;
+      const int2 e = vl[i];
+      if (c < 3) cp_async8(reinterpret_cast<double*>(dst + i * PIPE_VREC) + c, xg + 3 * (int64_t)e.x + c);
+      else cp_async16_ca(dst + i * PIPE_VREC + (c - 1), wv + e.y + 2 * (c - 3));
+    }
+  };
+  fetch_idx(0);
+  if (nj > 1) fetch_idx(1);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  fetch_inputs(0);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (int64_t j = 0; j < nj; ++j) {
+    const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
+    const int s = (int)(j % 3);
+    const TileHdr h = r_hdr[s];
+    const uint32_t loc = r_loc(s)[tid];
+    const uint32_t cm = r_cm(s)[tid];
+    double x[4][3], u[4][3], p[4];
+    int lead[4] = {0, 0, 0, 0};
+    {
+      const double2* tb = tab + (j & 1) * (PIPE_VCAP * PIPE_VREC);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = (loc >> (8 * a)) & 255;
+        const double2* rec = tb + i * PIPE_VREC;
+        const double2 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+        x[a][0] = q0.x; x[a][1] = q0.y; x[a][2] = q1.x;
+        u[a][0] = q2.x; u[a][1] = q2.y; u[a][2] = q3.x; p[a] = q3.y;
+        if (cm & INC_BC_BIT) lead[a] = r_vl(s)[i].y;   // first dofs are only needed by the Dirichlet path
+      }
+    }
+    if (h.nent > 0) tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+    cp_async_commit();                     // group A: tables(j)
+    if (j + 1 < nj) fetch_inputs(j + 1);
+    if (j + 2 < nj) fetch_idx(j + 2);
+    cp_async_commit();                     // group B: vertex table(j+1), index ring(j+2), header(j+2)
+    if (tid < h.ninc) phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
+    cp_async_wait_group<1>();              // tables(j)
+    __syncthreads();
+    if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+    cp_async_wait_all();                   // group B has had the whole tile to land
+    __syncthreads();                       // staging / tables are free again; table(j+1), ring(j+2), header(j+2) are visible
+  }
+}
+
+// ------------------------------------------------------------------------------------------ warp-specialised ring variant
+// One persistent CTA per SM, 384 threads: two compute warpgroups (phase A, 224 registers each) feed one helper warpgroup
+// (gather + stores, 56 registers) through a RING of three staging buffers.  The CTA's tiles form a sequence k = 0, 1, 2, ...
+// (tile blockIdx.x + k * gridDim.x); tile k is evaluated by compute group k % 2 into buffer k % 3 and drained by the helper
+// in order.  A compute group therefore never waits for the gather of its own previous tile (it only needs the helper to be
+// done with tile k - 3), and the helper never holds the big register budget: the three latency chains of a tile -- input
+// gathers, element algebra, reduction + stores -- overlap instead of adding up.  Hand-off: named barriers FULL[b] = 1 + b
+// (128 producers arrive, 128 helper threads sync) and EMPTY[b] = 4 + b (helper arrives, producers sync).
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+constexpr int WS_CAP = 128;    // incidences per tile (= threads of a compute group)
+constexpr int WS_ECAP = TILE_MAX_ENT;    // vertices per tile the trimmed tables hold
+constexpr int WS_NBUF = 3;
+constexpr size_t WS_VIEW = (TileSmem<WS_CAP, WS_ECAP>::bytes(true) + sizeof(TileHdr) + 15) & ~(size_t)15;   // + a copy of the tile header
+
 template <bool WANT_F>
 __global__ void __launch_bounds__(384, 1) k_p1tet_ws(P1_KERNEL_ARGS) {
-  constexpr int CAP = 128;
-  constexpr size_t VIEW = (TileSmem<CAP>::bytes(true) + 48 + 15) & ~(size_t)15;   // + a copy of the tile header
+  constexpr int CAP = WS_CAP;
+  using View = TileView<CAP, true, WS_ECAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wg = threadIdx.x >> 7;         // 0, 1: compute warpgroups; 2: helper
   const int tid = threadIdx.x & 127;
-  const int64_t stride = 2 * (int64_t)gridDim.x;
+  const int64_t nk = (n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA
   if (wg < 2) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const TileView<CAP, true> v(smem_raw + wg * VIEW);
-    TileHdr* s_hdr = reinterpret_cast<TileHdr*>(smem_raw + wg * VIEW + TileSmem<CAP>::bytes(true));
-    int k = 0;
-    for (int64_t tile = 2 * (int64_t)blockIdx.x + wg; tile < n_tiles; tile += stride, ++k) {
+    for (int64_t k = wg; k < nk; k += 2) {
+      const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
+      const int b = (int)(k % WS_NBUF);
+      const View v(smem_raw + b * WS_VIEW);
+      TileHdr* s_hdr = reinterpret_cast<TileHdr*>(smem_raw + b * WS_VIEW + TileSmem<CAP, WS_ECAP>::bytes(true));
       const int4 vt = inc_vtx[tile * CAP + tid];
       const int4 ld = inc_lead[tile * CAP + tid];
       const uint32_t cm = inc_cell[tile * CAP + tid];
       const TileHdr h = tile_hdr[tile];
-      if (k > 0) named_bar_sync(3 + wg, 256);            // EMPTY[wg]: the helper is done with the previous tile of this group
+      if (k + 2 < nk) {   // this group's next tile: pull its streaming inputs towards the SM
+        const int64_t nt = tile + 2 * (int64_t)gridDim.x;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_vtx + nt * CAP + tid));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_lead + nt * CAP + tid));
+        if ((tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_cell + nt * CAP + tid));
+        if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_hdr + nt));
+        if ((tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nt * CAP + tid));
+      }
+      if (k >= WS_NBUF) named_bar_sync(4 + b, 256);        // EMPTY[b]: the helper is done with tile k - 3
       if (h.nent > 0) tile_tables_async<CAP, CAP, true>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
       if (tid == 0) *s_hdr = h;
-      if (tid < h.ninc) phase_a<CAP, true, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, cell_bc, dbg);
+      if (tid < h.ninc) phase_a<CAP, true, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
       cp_async_wait_all();
       __threadfence_block();
-      named_bar_arrive(1 + wg, 256);                      // FULL[wg]
+      named_bar_arrive(1 + b, 256);                         // FULL[b]
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    for (int64_t base = 2 * (int64_t)blockIdx.x; base < n_tiles; base += stride) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int64_t tile = base + g;
-        if (tile >= n_tiles) continue;
-        const TileView<CAP, true> v(smem_raw + g * VIEW);
-        const TileHdr* s_hdr = reinterpret_cast<const TileHdr*>(smem_raw + g * VIEW + TileSmem<CAP>::bytes(true));
-        named_bar_sync(1 + g, 256);                       // FULL[g]
-        const TileHdr h = *s_hdr;
-        if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, true, WANT_F>(v, h, tid, vals, F);
-        if (tile + stride < n_tiles) named_bar_arrive(3 + g, 256);   // EMPTY[g] (nobody waits after the group's last tile)
+    for (int64_t k = 0; k < nk; ++k) {
+      const int b = (int)(k % WS_NBUF);
+      const View v(smem_raw + b * WS_VIEW);
+      const TileHdr* s_hdr = reinterpret_cast<const TileHdr*>(smem_raw + b * WS_VIEW + TileSmem<CAP, WS_ECAP>::bytes(true));
+      if ((dbg & 16) && k + 4 < nk) {   // experiment: pull the gather lines (coordinates, state) of a tile two rounds ahead into L2
+        const int64_t nt = (int64_t)blockIdx.x + (k + 4) * gridDim.x;
+        const int4 pv = inc_vtx[nt * CAP + tid];
+        const int4 pl = inc_lead[nt * CAP + tid];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.y));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.z));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.w));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.y));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.z));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.w));
       }
+      named_bar_sync(1 + b, 256);                           // FULL[b]
+      const TileHdr h = *s_hdr;
+      if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, true, WANT_F>(v, h, tid, vals, F);
+      if (k + WS_NBUF < nk) named_bar_arrive(4 + b, 256);   // EMPTY[b] (nobody waits after the buffer's last tile)
     }
   }
 }
@@ -607,7 +795,7 @@ __global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
     }
     double blk[16], fr[4];
     const bool row_is_origin = (cm & 3u) == 0;
-    const bool has_bc = has_inc && cell_bc && cell_bc[cm >> 2];
+    const bool has_bc = has_inc && (cm & INC_BC_BIT) != 0;
     // lifting needs the Jacobian rows even in a residual-only pass; BC cells are rare, so the branch is cheap
     if (WANT_J) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
     else if (__any_sync(0xffffffffu, has_bc)) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
@@ -653,8 +841,8 @@ __global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
         {
-          v.stageJ[(j * 8 + 2 * r) * CAP + inc] = make_double2(blk[4 * r], blk[4 * r + 1]);
-          v.stageJ[(j * 8 + 2 * r + 1) * CAP + inc] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
+          v.stageJ[stage_idx(CAP, j, 2 * r, inc)] = make_double2(blk[4 * r], blk[4 * r + 1]);
+          v.stageJ[stage_idx(CAP, j, 2 * r + 1, inc)] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
         }
       }
       if (WANT_F && j == 0) v.stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
@@ -730,8 +918,8 @@ int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
 void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) return;
-  cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
-  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_cell_bc); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
+  cudaFree(P->d_tile_vlist); cudaFree(P->d_inc_loc); cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
+  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
   delete P;
   ctx->p1plan = nullptr;
 }
@@ -773,7 +961,8 @@ template <typename K> static cudaError_t smem_attr(K kernel, size_t bytes) {
     else if (cap == 192) { OP((k_p1tet_tiles<192, 1, true, true>), (k_p1tet_tiles<192, 1, true, false>), (k_p1tet_tiles<192, 1, false, true>), 192, 192); } \
     else if (cap == 128) { OP((k_p1tet_tiles<128, 2, true, true>), (k_p1tet_tiles<128, 2, true, false>), (k_p1tet_tiles<128, 2, false, true>), 128, 128); } \
     else if (cap == 96) { OP((k_p1tet_tiles<96, 3, true, true>), (k_p1tet_tiles<96, 3, true, false>), (k_p1tet_tiles<96, 3, false, true>), 96, 96); } \
-    else { OP((k_p1tet_tiles<64, 4, true, true>), (k_p1tet_tiles<64, 4, true, false>), (k_p1tet_tiles<64, 4, false, true>), 64, 64); }             \
+    else if (cap == 64) { OP((k_p1tet_tiles<64, 4, true, true>), (k_p1tet_tiles<64, 4, true, false>), (k_p1tet_tiles<64, 4, false, true>), 64, 64); }   \
+    else { OP((k_p1tet_tiles<32, 8, true, true>), (k_p1tet_tiles<32, 8, true, false>), (k_p1tet_tiles<32, 8, false, true>), 32, 32); }             \
   }
 
 int p1tet_build_plan(nsgpu_ctx* ctx) {
@@ -792,7 +981,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   int64_t *d_tile_ent = nullptr, *d_tsize = nullptr, *d_boff = nullptr;
   int* d_slot_cnt = nullptr;
   void* d_tmp = nullptr;
-  int* d_flag = nullptr;   // [0] bad, [1] not contiguous
+  int* d_flag = nullptr;   // [0] bad, [1] not contiguous, [2] most vertices in one tile, [3] most distinct mesh vertices touched by one tile
   auto cleanup = [&]() {
     cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_items); cudaFree(d_items2); cudaFree(d_leader); cudaFree(c_cell); cudaFree(c_vtx);
     cudaFree(c_lead); cudaFree(c_src); cudaFree(d_slot_start); cudaFree(d_diag); cudaFree(d_cnt); cudaFree(d_nrun); cudaFree(d_nslots);
@@ -859,7 +1048,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_tmp); d_tmp = nullptr;
   P->maxdeg = (int)maxdeg;
-  if (maxdeg > 63 || maxdeg > CAPV / 2) {   // pathological vertex degree: keep the generic path
+  if (maxdeg > 63 || maxdeg > (CAPV >= 64 ? CAPV / 2 : CAPV)) {   // pathological vertex degree: keep the generic path
     cleanup();
     ctx->p1plan = P; p1tet_free(ctx);
     return NSGPU_EUNSUPPORTED;
@@ -868,8 +1057,8 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_SCAN(d_cnt, d_inc_ptr, n_ent + 1);
 
   // per-vertex output info and neighbour-slot prefix
-  PL_CUDA(cudaMalloc(&d_flag, 2 * sizeof(int)));
-  PL_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), s));
+  PL_CUDA(cudaMalloc(&d_flag, 4 * sizeof(int)));
+  PL_CUDA(cudaMemsetAsync(d_flag, 0, 4 * sizeof(int), s));
   PL_CUDA(cudaMalloc(&d_nslots, sizeof(int64_t) * (n_ent + 1)));
   PL_CUDA(cudaMalloc(&d_slot_ptr, sizeof(int64_t) * (n_ent + 1)));
   PL_CUDA(cudaMalloc(&d_diag, n_ent + 1));
@@ -913,15 +1102,27 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_items2); d_items2 = nullptr;
 
-  // tiles: vertex e belongs to tile floor(inc_ptr[e] / capeff); then the tile-padded / packed arrays
-  const int64_t capeff = CAPV - maxdeg + 1;
-  const int64_t n_tiles = ceil_div(n_inc, capeff);
+  // tiles: consecutive vertices packed greedily -- a tile closes when the next vertex's incidences would not fit the CAPV
+  // lanes any more (or at TILE_MAX_ENT vertices, which keeps the per-vertex tables of the trimmed kernels small).  The scan
+  // is inherently sequential but trivial, so it runs on the host over the incidence prefix (8 bytes per vertex, one-off).
+  std::vector<int64_t> h_inc_ptr((size_t)n_ent + 1), h_tile_ent;
+  PL_CUDA(cudaMemcpy(h_inc_ptr.data(), d_inc_ptr, sizeof(int64_t) * (n_ent + 1), cudaMemcpyDeviceToHost));
+  h_tile_ent.reserve((size_t)(n_inc / (CAPV > 16 ? CAPV - 16 : 1)) + 16);
+  for (int64_t e = 0; e < n_ent;) {
+    h_tile_ent.push_back(e);
+    const int64_t i0 = h_inc_ptr[e];
+    int64_t e1 = e + 1;
+    while (e1 < n_ent && h_inc_ptr[e1 + 1] - i0 <= CAPV && e1 - e < TILE_MAX_ENT) ++e1;
+    e = e1;
+  }
+  const int64_t n_tiles = (int64_t)h_tile_ent.size();
+  h_tile_ent.push_back(n_ent);
   P->n_tiles = n_tiles;
   PL_CUDA(cudaMalloc(&d_tile_ent, sizeof(int64_t) * (n_tiles + 1)));
-  k_tiles<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, n_ent, capeff, d_inc_ptr, d_tile_ent);
+  PL_CUDA(cudaMemcpy(d_tile_ent, h_tile_ent.data(), sizeof(int64_t) * (n_tiles + 1), cudaMemcpyHostToDevice));
   PL_CUDA(cudaMalloc(&d_tsize, sizeof(int64_t) * (n_tiles + 1)));
   PL_CUDA(cudaMalloc(&d_boff, sizeof(int64_t) * (n_tiles + 1)));
-  k_tile_sizes<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, d_tile_ent, d_slot_ptr, d_tsize);
+  k_tile_sizes<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, d_tile_ent, d_slot_ptr, d_tsize, d_flag + 2);
   PL_SCAN(d_tsize, d_boff, n_tiles + 1);
   int64_t n_bytes = 0;
   PL_CUDA(cudaMemcpy(&n_bytes, d_boff + n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -936,9 +1137,14 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   k_tile_pack<<<(unsigned)n_tiles, 128, 0, s>>>(CAPV, d_tile_ent, d_inc_ptr, d_slot_ptr, d_boff, c_cell, c_vtx, c_lead,
                                                 reinterpret_cast<const uint32_t*>(c_src), d_slot_start, d_diag, P->d_tile_hdr, P->d_ent_rel,
                                                 P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes);
-  PL_CUDA(cudaMalloc(&P->d_cell_bc, ctx->n_cells_owned > 0 ? ctx->n_cells_owned : 1));
-  int flags[2] = {0, 0};
-  PL_CUDA(cudaMemcpyAsync(flags, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (CAPV == 128) {
+    PL_CUDA(cudaMalloc(&P->d_tile_vlist, sizeof(int2) * (size_t)n_tiles * PIPE_VCAP));
+    PL_CUDA(cudaMemsetAsync(P->d_tile_vlist, 0, sizeof(int2) * (size_t)n_tiles * PIPE_VCAP, s));
+    PL_CUDA(cudaMalloc(&P->d_inc_loc, sizeof(uint32_t) * (size_t)n_tiles * CAPV));
+    k_tile_vlist<<<(unsigned)n_tiles, 128, 0, s>>>(P->d_tile_hdr, P->d_inc_vtx, P->d_inc_lead, P->d_tile_vlist, P->d_inc_loc, d_flag + 3);
+  }
+  int flags[4] = {0, 0, 0, 0};
+  PL_CUDA(cudaMemcpyAsync(flags, d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PL_CUDA(cudaStreamSynchronize(s));
   PL_CUDA(cudaGetLastError());
   ctx->launches += 18;
@@ -948,6 +1154,8 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
     return NSGPU_EUNSUPPORTED;
   }
   P->contiguous = flags[1] == 0;
+  P->max_nent = flags[2];
+  P->max_nv = flags[3];
   P->bc_dirty = true;
   ctx->p1plan = P;
   const int lanes = ctx->lanes, cap = CAPV;
@@ -969,40 +1177,67 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   if (!P) { set_error(ctx, "p1tet plan missing"); return NSGPU_EINVAL; }
   cudaStream_t s = ctx->stream;
   if (P->n_tiles == 0) return NSGPU_OK;
-  if (ctx->has_bc && P->bc_dirty) {
-    k_cell_bc<<<g256(ctx->n_cells_owned), 256, 0, s>>>(ctx->n_cells_owned, ctx->d_dofmap, ctx->d_bc_marker, P->d_cell_bc);
+  if (P->bc_dirty) {
+    k_inc_bc<<<g256(P->n_tiles * P->cap), 256, 0, s>>>(P->n_tiles * P->cap, P->d_inc_cell, ctx->d_dofmap, ctx->has_bc ? ctx->d_bc_marker : nullptr);
     P->bc_dirty = false;
     ctx->launches += 1;
   }
-  const uint8_t* cbc = ctx->has_bc ? P->d_cell_bc : nullptr;
   const int lanes = ctx->lanes, cap = P->cap;
-  if (ctx->ws && want_J && lanes == 1 && cap == 128) {
-    // warp-specialised persistent kernel: one CTA per SM
-    constexpr size_t VIEW = (TileSmem<128>::bytes(true) + 48 + 15) & ~(size_t)15;
-    const unsigned grid = (unsigned)(ctx->n_sms < (P->n_tiles + 1) / 2 ? ctx->n_sms : (P->n_tiles + 1) / 2);
+  if (ctx->pipe && !ctx->ws && lanes == 1 && cap == 128 && P->contiguous && P->max_nent <= PIPE_ECAP && P->max_nv <= PIPE_VCAP && P->d_tile_vlist) {
+    // software-pipelined persistent kernel, 2 CTAs/SM
+    static int pipe_occ = 0;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2)
+    if (!pipe_occ) {
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<false>::bytes));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      int occ = 0;
+      NS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p1tet_pipe<true, true>, 128, PipeSmem<true>::bytes));
+      pipe_occ = occ > 0 ? (occ > 2 ? 2 : occ) : 1;
+      if (getenv("NSGPU_VERBOSE")) fprintf(stderr, "[nsgpu] k_p1tet_pipe: %zu B smem, %d CTA/SM\n", PipeSmem<true>::bytes, occ);
+    }
+    const int64_t resident = (int64_t)pipe_occ * ctx->n_sms;
+    const unsigned grid = (unsigned)(resident < P->n_tiles ? resident : P->n_tiles);
+#define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
+                     P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
+                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles, P->d_tile_vlist, P->d_inc_loc
+    if (want_J && want_F) k_p1tet_pipe<true, true><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
+    else if (want_J) k_p1tet_pipe<true, false><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
+    else k_p1tet_pipe<false, true><<<grid, 128, PipeSmem<false>::bytes, s>>>(P1_PIPE_ARGS);
+#undef P1_PIPE_ARGS
+    ctx->launches += 1;
+    NS_CUDA(ctx, cudaGetLastError());
+    return NSGPU_OK;
+  }
+  if (ctx->ws && want_J && lanes == 1 && cap == WS_CAP && P->max_nent <= WS_ECAP) {
+    // warp-specialised persistent ring kernel: one CTA per SM
+    constexpr size_t SMEM = WS_NBUF * WS_VIEW;
+    const unsigned grid = (unsigned)(ctx->n_sms < P->n_tiles ? ctx->n_sms : P->n_tiles);
     static bool attr_set = false;
     if (!attr_set) {
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * VIEW)));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * VIEW)));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
       attr_set = true;
     }
     if (want_F)
-      k_p1tet_ws<true><<<grid, 384, 2 * VIEW, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc,
+      k_p1tet_ws<true><<<grid, 384, SMEM, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value,
           P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
           reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
     else
-      k_p1tet_ws<false><<<grid, 384, 2 * VIEW, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc,
+      k_p1tet_ws<false><<<grid, 384, SMEM, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value,
           P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
           reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
     ctx->launches += 1;
     NS_CUDA(ctx, cudaGetLastError());
     return NSGPU_OK;
   }
-#define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, cbc, P->d_inc_cell, \
+#define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
                 reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles
   // one-thread kernels are persistent (grid = resident CTAs); the quad kernels take one tile per CTA
-  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 96 ? 3 : (cap == 64 ? 4 : 1)));
+  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 96 ? 3 : (cap == 64 ? 4 : (cap == 32 ? 8 : 1))));
   const unsigned grid = (unsigned)((lanes == 4 || ctx->persistent == 0) ? P->n_tiles : (resident < P->n_tiles ? resident : P->n_tiles));
 #define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
   if (want_J && want_F) KJF<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                        \

@@ -86,11 +86,12 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     asm.close()
 
 
-@pytest.mark.parametrize("kernel,lanes,threads,ws", [(1, 1, 128, 0), (2, 1, 64, 0), (2, 1, 128, 0), (2, 1, 128, 1), (2, 1, 192, 0), (2, 1, 256, 0),
-                                                      (2, 4, 256, 0), (2, 4, 384, 0), (2, 4, 512, 0)])
-def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads, ws):
+@pytest.mark.parametrize("kernel,lanes,threads,ws,pipe", [(1, 1, 128, 0, 0), (2, 1, 64, 0, 0), (2, 1, 128, 0, 0), (2, 1, 128, 0, 1), (2, 1, 128, 1, 0),
+                                                           (2, 1, 192, 0, 0), (2, 1, 256, 0, 0), (2, 4, 256, 0, 0), (2, 4, 384, 0, 0), (2, 4, 512, 0, 0)])
+def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads, ws, pipe):
     """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernel, which must apply;
-    lanes 1: one thread per incidence, lanes 4: four lanes per incidence."""
+    lanes 1: one thread per incidence, lanes 4: four lanes per incidence; ws: warp-specialised ring variant;
+    pipe: software-pipelined variant (the default)."""
     m, sp, w, bcs, fk = _case("duct_p1")
     w = w + 0.01 * np.random.default_rng(4).standard_normal(sp.n_dofs)     # off the Dirichlet values: lifting active
     indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
@@ -98,6 +99,7 @@ def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads, ws):
     asm.set_option("lanes", lanes)
     asm.set_option("threads", threads)
     asm.set_option("ws", ws)
+    asm.set_option("pipe", pipe)
     asm.create_matrix(fetch=False)
     gv, gF = asm.jacobian_residual(w)
     assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
