@@ -376,14 +376,25 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
       double4 acc[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] = make_double4(0.0, 0.0, 0.0, 0.0);
-      for (int q = jb; q < je; ++q) {
-        const int code = sp[q];
-        const int ii = rel.x + (code >> 2), a = code & 3;
-        const double2* blkp = v.stageJ + a * 8 * CAP + ii;
+      // three parked blocks per round: their list bytes, then all 24 pieces, are fetched before the first add, so the
+      // shared-memory latency is paid once per round instead of once per block (registers are plentiful in this phase).
+      // Missing blocks of the last round are predicated-off loads into zeroed registers: measured faster than a scalar tail.
+      for (int q = jb; q < je; q += 3) {
+        double2 t[3][8];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const bool ok = q + i < je;
+          const int code = ok ? sp[q + i] : 0;
+          const double2* blkp = v.stageJ + (code & 3) * 8 * CAP + rel.x + (code >> 2);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[i][k] = ok ? blkp[k * CAP] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double2 lo = blkp[(2 * r) * CAP], hi = blkp[(2 * r + 1) * CAP];
-          acc[r].x += lo.x; acc[r].y += lo.y; acc[r].z += hi.x; acc[r].w += hi.y;
+          acc[r].x += (t[0][2 * r].x + t[1][2 * r].x) + t[2][2 * r].x;
+          acc[r].y += (t[0][2 * r].y + t[1][2 * r].y) + t[2][2 * r].y;
+          acc[r].z += (t[0][2 * r + 1].x + t[1][2 * r + 1].x) + t[2][2 * r + 1].x;
+          acc[r].w += (t[0][2 * r + 1].y + t[1][2 * r + 1].y) + t[2][2 * r + 1].y;
         }
       }
 #pragma unroll
@@ -405,12 +416,24 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
       double accF = 0.0;
       if (le < h.nent) {
         const int ib = v.rel[le].x, ie = v.rel[le + 1].x;
-        for (int ii = ib + part; ii < ie; ii += 4) {
-          if (WANT_J) {
-            const double2 lo = v.stageJ[(2 * r) * CAP + ii], hi = v.stageJ[(2 * r + 1) * CAP + ii];
-            acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+        for (int ii = ib + part; ii < ie; ii += 12) {   // three incidences per round, loads first
+          double2 lo[3], hi[3];
+          double f[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int i2 = ii + 4 * i;
+            const bool ok = i2 < ie;
+            if (WANT_J) {
+              lo[i] = ok ? v.stageJ[(2 * r) * CAP + i2] : make_double2(0.0, 0.0);
+              hi[i] = ok ? v.stageJ[(2 * r + 1) * CAP + i2] : make_double2(0.0, 0.0);
+            }
+            if (WANT_F) f[i] = ok ? sf[4 * i2 + r] : 0.0;
           }
-          if (WANT_F) accF += sf[4 * ii + r];
+          if (WANT_J) {
+            acc.x += (lo[0].x + lo[1].x) + lo[2].x; acc.y += (lo[0].y + lo[1].y) + lo[2].y;
+            acc.z += (hi[0].x + hi[1].x) + hi[2].x; acc.w += (hi[0].y + hi[1].y) + hi[2].y;
+          }
+          if (WANT_F) accF += (f[0] + f[1]) + f[2];
         }
       }
       if (WANT_J) { acc.x = quad_sum_b(acc.x); acc.y = quad_sum_b(acc.y); acc.z = quad_sum_b(acc.z); acc.w = quad_sum_b(acc.w); }
