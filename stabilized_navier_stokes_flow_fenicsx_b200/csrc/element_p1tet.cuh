@@ -261,8 +261,16 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
   for (int j = 0; j < 3; ++j) P[j] = p[0] * g[0][j] + p[1] * g[1][j] + p[2] * g[2][j] + p[3] * g[3][j];
   const double divu = D[0][0] + D[1][1] + D[2][2];
 
+  // row-vertex constants needed inside the point loop: H = D g_0 and P . g_0, so that the SUPG weight a_0(q) = r_q . g_0
+  // (r_q = grad p + u_q . grad u) is P.g_0 + H.u_q -- the residual vector r_q itself is never formed
+  double H[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) H[d] = D[d][0] * g[0][0] + D[d][1] * g[0][1] + D[d][2] * g[0][2];
+  const double Pg0 = P[0] * g[0][0] + P[1] * g[0][1] + P[2] * g[0][2];
+
   // ---- quadrature points: totals stay in registers, the data of points 1..3 is parked ----
-  double s[3] = {0, 0, 0}, Q[6] = {0, 0, 0, 0, 0, 0}, ZG[3] = {0, 0, 0}, TR[3] = {0, 0, 0}, Y3[3] = {0, 0, 0}, sup[3] = {0, 0, 0};
+  // (sum_q W tau r_q and sum_q W tau G u_q follow from s = sum_q W tau u_q after the loop: both are linear in u_q)
+  double s[3] = {0, 0, 0}, Q[6] = {0, 0, 0, 0, 0, 0}, Y3[3] = {0, 0, 0}, sup[3] = {0, 0, 0};
   double Y1[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double tbar = 0.0, nuLbar = 0.0;
   P1TetPoint pt0;
@@ -270,7 +278,6 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     P1TetPoint pt;
-    double r[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) pt.uq[i] = P1T_A * U[i] + P1T_E * u[q][i];
     pt.Gu[0] = G[0] * pt.uq[0] + G[1] * pt.uq[1] + G[2] * pt.uq[2];
@@ -279,9 +286,7 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
     const double arg = Cst + pt.uq[0] * pt.Gu[0] + pt.uq[1] * pt.Gu[1] + pt.uq[2] * pt.Gu[2];
     const double tau = NS_RSQRT(arg);
     const double wt = W * tau;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) r[j] = P[j] + pt.uq[0] * D[0][j] + pt.uq[1] * D[1][j] + pt.uq[2] * D[2][j];
-    const double al = wt * (r[0] * g[0][0] + r[1] * g[0][1] + r[2] * g[0][2]);
+    const double al = wt * (Pg0 + H[0] * pt.uq[0] + H[1] * pt.uq[1] + H[2] * pt.uq[2]);
     const double be = al * tau * tau;
     pt.ew = P1T_E * wt; pt.eb = P1T_E * be; pt.ea = P1T_E * al;
     tbar += wt;
@@ -289,8 +294,6 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       s[i] += wt * pt.uq[i];
-      ZG[i] += wt * pt.Gu[i];
-      TR[i] += wt * r[i];
       Y3[i] += be * pt.Gu[i];
       if (WANT_F) sup[i] += al * pt.uq[i];
     }
@@ -317,10 +320,7 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
   }
   nuLbar *= itrG;
 
-  double H[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) H[d] = D[d][0] * g[0][0] + D[d][1] * g[0][1] + D[d][2] * g[0][2];
-  const double TR0 = TR[0] * g[0][0] + TR[1] * g[0][1] + TR[2] * g[0][2];
+  const double TR0 = tbar * Pg0 + H[0] * s[0] + H[1] * s[1] + H[2] * s[2];   // (sum_q W tau r_q) . g_0
 
   if (WANT_F) {
     const double pbarV = W * (p[0] + p[1] + p[2] + p[3]);
@@ -335,6 +335,8 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
     const double M_off = W * (4.0 * P1T_A * P1T_A + 2.0 * P1T_A * P1T_E);
     const double akap = P1T_A * kap;
     // column-vertex independent parts
+    const double ZG[3] = {G[0] * s[0] + G[1] * s[1] + G[2] * s[2], G[1] * s[0] + G[3] * s[1] + G[4] * s[2],
+                          G[2] * s[0] + G[4] * s[1] + G[5] * s[2]};   // sum_q W tau G u_q = G s
     double C0[3][3], P0[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)

@@ -639,20 +639,20 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
   unsigned char* ring = smem_raw + PS::view + 2 * PS::table;                          // [3] { int2 vl[PIPE_VCAP]; u32 loc[CAP]; u32 cm[CAP]; }
   TileHdr* r_hdr = reinterpret_cast<TileHdr*>(ring + 3 * PS::ring);                   // [3]
   const int tid = threadIdx.x;
-  const int64_t nj = (n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int nj = (int)((n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA (32-bit loop state: registers are scarce)
   auto r_vl = [&](int s) { return reinterpret_cast<int2*>(ring + s * PS::ring); };
   auto r_loc = [&](int s) { return reinterpret_cast<uint32_t*>(ring + s * PS::ring + PIPE_VCAP * sizeof(int2)); };
   auto r_cm = [&](int s) { return r_loc(s) + CAP; };
-  auto fetch_idx = [&](const int64_t j) {
-    const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
-    const int s = (int)(j % 3);
+  auto fetch_idx = [&](const int j) {
+    const int64_t t = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+    const int s = j % 3;
     cp_async8(r_vl(s) + tid, tile_vlist + t * PIPE_VCAP + tid);
     cp_async4(r_loc(s) + tid, inc_loc + t * CAP + tid);
     cp_async4(r_cm(s) + tid, inc_cell + t * CAP + tid);
     if (tid < 2) cp_async16(reinterpret_cast<unsigned char*>(r_hdr + s) + 16 * tid, reinterpret_cast<const unsigned char*>(tile_hdr + t) + 16 * tid);
   };
-  auto fetch_inputs = [&](const int64_t j) {   // the header and vertex list of tile j are already visible in their ring slots
-    const int s = (int)(j % 3);
+  auto fetch_inputs = [&](const int j) {   // the header and vertex list of tile j are already visible in their ring slots
+    const int s = j % 3;
     const int n = r_hdr[s].nv * PIPE_VREC;
     double2* dst = tab + (j & 1) * (PIPE_VCAP * PIPE_VREC);
     const int2* vl = r_vl(s);
@@ -672,9 +672,9 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  for (int64_t j = 0; j < nj; ++j) {
-    const int64_t tile = (int64_t)blockIdx.x + j * gridDim.x;
-    const int s = (int)(j % 3);
+  for (int j = 0; j < nj; ++j) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+    const int s = j % 3;
     const TileHdr h = r_hdr[s];
     const uint32_t loc = r_loc(s)[tid];
     const uint32_t cm = r_cm(s)[tid];
