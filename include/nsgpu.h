@@ -114,6 +114,23 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
  * y_owned = J x with the Jacobian of the last nsgpu_jacobian*; x: n_owned (+ghost, refreshed by the halo). */
 int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned);
 
+/* KSPSolve with KSPTFQMR (snes_ksp_type 'tfqmr', NavierStokesChannelFlow.py:77, :282-283; KSP rtol :285) on the
+ * Jacobian of the last nsgpu_jacobian*: transpose-free QMR, right-preconditioned, every vector and scalar
+ * device-resident; two MatMults per iteration, dot products reduced over all ranks (ncclAllReduce).
+ *   pc: 0 none, 1 Jacobi, 4 = 4x4 block Jacobi over the dofs of one P1-P1 vertex (falls back to 1 elsewhere).
+ *   zero_guess != 0 ignores the incoming x (PETSc's default initial guess).
+ * Stops when the quasi-residual bound tau*sqrt(m+1) <= max(rtol * ||b||, atol) (PETSc's default test) or after max_it iterations;
+ * *its_out = iterations done, *rnorm_out = TRUE residual norm ||b - A x|| at exit, *r0norm_out = ||b - A x0||.
+ * b: n_owned values; x: host variant n_owned in/out, device variant n_owned + n_ghost (+ column ghosts) values. */
+int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double rtol, double atol, int max_it, int pc, int zero_guess,
+                int* its_out, double* rnorm_out, double* r0norm_out);
+int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_dev, double rtol, double atol, int max_it, int pc,
+                    int zero_guess, int* its_out, double* rnorm_out, double* r0norm_out);
+/* The two vector operations a device-resident Newton loop needs besides F, J and the solve (VecAXPY / VecNorm on
+ * the owned entries; the norm is reduced over all ranks): y += a x, *out = ||x||_2. */
+int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev);
+int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out);
+
 /* Replace the matrix values (e.g. to use nsgpu_spmv with a matrix assembled elsewhere). */
 int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals);
 int nsgpu_get_values(nsgpu_ctx* ctx, double* vals);
@@ -134,8 +151,10 @@ int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_
 int nsgpu_host_alloc_pinned(int64_t bytes, void** out);
 int nsgpu_host_free_pinned(void* p);
 
-/* Options: "kernel" (NSGPU_KERNEL_*); for the factorised kernel "lanes" (1 or 4 lanes per vertex-cell incidence) and
- * "threads" (CTA size: 64..256 with 1 lane, 256..512 with 4 lanes). */
+/* Options: "kernel" (NSGPU_KERNEL_*); for the factorised kernel "pipe" (1, default: software-pipelined variant whose
+ * inputs arrive through cp.async one tile ahead), "ws" (1: warp-specialised ring variant), "lanes" (1 or 4 lanes per
+ * vertex-cell incidence), "threads" (CTA size: 64..256 with 1 lane, 256..512 with 4 lanes), "persistent", and "debug"
+ * (timing experiments only). */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.

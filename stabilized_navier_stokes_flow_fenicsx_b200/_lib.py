@@ -39,6 +39,12 @@ SIGNATURES = {
     "nsgpu_jacobian": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p]),
     "nsgpu_jacobian_residual": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nsgpu_spmv": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p]),
+    "nsgpu_tfqmr": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_int), c_f64p, c_f64p]),
+    "nsgpu_tfqmr_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_int), c_f64p, c_f64p]),
+    "nsgpu_axpy_dev": (ctypes.c_int, [c_ctx, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "nsgpu_norm_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, c_f64p]),
     "nsgpu_set_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),
     "nsgpu_get_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),
     "nsgpu_jacobian_residual_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),

@@ -180,6 +180,52 @@ class NSAssembler:
         self._check(self.lib.nsgpu_spmv(self.ctx, _ptr(x), _ptr(out)), "spmv")
         return out
 
+    def tfqmr(self, b, x0=None, rtol=1e-8, atol=0.0, max_it=1000, pc=4):
+        """KSPSolve with KSPTFQMR on the resident Jacobian (NavierStokesChannelFlow.py:77, :282-285), fully on the device.
+        Returns (x_owned, info) with info = dict(its, rnorm = true ||b - A x||, r0norm)."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(self.n_owned) if x0 is None else np.array(x0[: self.n_owned], dtype=np.float64)
+        its, rn, r0 = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        self._check(self.lib.nsgpu_tfqmr(self.ctx, _ptr(b), _ptr(x), float(rtol), float(atol), int(max_it), int(pc), 1 if x0 is None else 0,
+                                         ctypes.byref(its), ctypes.byref(rn), ctypes.byref(r0)), "tfqmr")
+        return x, {"its": its.value, "rnorm": rn.value, "r0norm": r0.value}
+
+    def tfqmr_dev(self, b_dev, x_dev, rtol=1e-8, atol=0.0, max_it=1000, pc=4, zero_guess=True):
+        its, rn, r0 = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        self._check(self.lib.nsgpu_tfqmr_dev(self.ctx, b_dev, x_dev, float(rtol), float(atol), int(max_it), int(pc), 1 if zero_guess else 0,
+                                             ctypes.byref(its), ctypes.byref(rn), ctypes.byref(r0)), "tfqmr_dev")
+        return {"its": its.value, "rnorm": rn.value, "r0norm": r0.value}
+
+    def axpy_dev(self, a, x_dev, y_dev):
+        self._check(self.lib.nsgpu_axpy_dev(self.ctx, float(a), x_dev, y_dev), "axpy_dev")
+
+    def norm_dev(self, x_dev):
+        out = ctypes.c_double()
+        self._check(self.lib.nsgpu_norm_dev(self.ctx, x_dev, ctypes.byref(out)), "norm_dev")
+        return out.value
+
+    def newton_dev(self, w_dev, rtol=1e-8, atol=1e-8, max_it=30, ksp_rtol=1e-8, ksp_max_it=2000, pc=4, work=None):
+        """Device-resident Newton iteration with the SNES settings of the reference (snes_rtol / snes_atol 1e-8, max_it 30,
+        NavierStokesChannelFlow.py:286-291; basic line search): F and J from the assembly kernels, dw from TFQMR, w -= dw.
+        Nothing but a few scalars crosses PCIe.  w_dev: n_cols doubles (state in / solution out).  Returns the history."""
+        nbytes = 8 * self.n_cols
+        F_dev, dw_dev = work if work is not None else (self.dev_alloc(nbytes), self.dev_alloc(nbytes))
+        hist = []
+        try:
+            for it in range(max_it + 1):
+                self.jacobian_residual_dev(w_dev, True, F_dev)
+                fn = self.norm_dev(F_dev)
+                hist.append({"it": it, "fnorm": fn})
+                if fn <= atol or (it > 0 and fn <= rtol * hist[0]["fnorm"]) or it == max_it:
+                    break
+                info = self.tfqmr_dev(F_dev, dw_dev, rtol=ksp_rtol, max_it=ksp_max_it, pc=pc)
+                hist[-1].update(ksp_its=info["its"], ksp_rnorm=info["rnorm"])
+                self.axpy_dev(-1.0, dw_dev, w_dev)
+        finally:
+            if work is None:
+                self.dev_free(F_dev); self.dev_free(dw_dev)
+        return hist
+
     def set_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         self._check(self.lib.nsgpu_set_values(self.ctx, _ptr(vals)), "set_values")

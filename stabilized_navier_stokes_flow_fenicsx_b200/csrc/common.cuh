@@ -80,6 +80,7 @@ struct nsgpu_ctx {
   int32_t* d_members = nullptr;     // [leader dof][KMAX] member dofs
   bool rows_presorted = false;      // column blocks of each row are contiguous per neighbour entity, in pair order
   struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
+  void* krylov = nullptr;                      // work vectors of the device-resident TFQMR (krylov.cu)
 
   // work vectors (n_dofs)
   double* d_xvec = nullptr;
@@ -147,5 +148,12 @@ int halo_forward(nsgpu_ctx* ctx, double* d_v);
 int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);
 int rows_exchange_add(nsgpu_ctx* ctx);
 void halo_free(nsgpu_ctx* ctx);
+int allreduce_sum(nsgpu_ctx* ctx, double* d_buf, int n);
+// krylov.cu
+int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, double atol, int max_it, int pc, bool zero_guess, int* its_out,
+               double* rnorm_out, double* r0norm_out);
+int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y);
+int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
+void krylov_free(nsgpu_ctx* ctx);
 
 }  // namespace nsgpu

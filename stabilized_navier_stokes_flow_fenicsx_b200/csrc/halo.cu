@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -39,7 +40,7 @@ static NcclApi* nccl_api(std::string* why) {
     if (api.handle) {
 #define NS_SYM(f) api.f = (decltype(api.f))dlsym(api.handle, "nccl" #f)
       NS_SYM(GetUniqueId); NS_SYM(CommInitRank); NS_SYM(CommDestroy); NS_SYM(GroupStart); NS_SYM(GroupEnd);
-      NS_SYM(Send); NS_SYM(Recv); NS_SYM(GetErrorString);
+      NS_SYM(Send); NS_SYM(Recv); NS_SYM(AllReduce); NS_SYM(GetErrorString);
 #undef NS_SYM
     }
   }
@@ -96,6 +97,16 @@ static int exchange(nsgpu_ctx* ctx, const std::vector<int>& ranks, const std::ve
     if (nr > 0) NS_NCCL(ctx, api, api->Recv(rbuf + rptr[k], (size_t)nr, ncclFloat64, ranks[k], comm, ctx->stream));
   }
   NS_NCCL(ctx, api, api->GroupEnd());
+  return NSGPU_OK;
+}
+
+// in-place sum over all ranks (Krylov dot products); in-stream, no host synchronisation
+int allreduce_sum(nsgpu_ctx* ctx, double* d_buf, int n) {
+  if (ctx->nranks <= 1) return NSGPU_OK;
+  std::string why;
+  NcclApi* api = nccl_api(&why);
+  if (!api || !api->AllReduce || !ctx->nccl_comm) { set_error(ctx, "allreduce without a communicator"); return NSGPU_ENCCL; }
+  NS_NCCL(ctx, api, api->AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   return NSGPU_OK;
 }
 

@@ -73,6 +73,7 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_xvec); cudaFree(ctx->d_F); cudaFree(ctx->d_y);
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
+  krylov_free(ctx);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   if (ctx->tev[0]) cudaEventDestroy(ctx->tev[0]);
@@ -357,6 +358,45 @@ int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned) {
   NS_CUDA(ctx, cudaMemcpyAsync(y_owned, ctx->d_y, sizeof(double) * ctx->n_owned, cudaMemcpyDeviceToHost, s));
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return elapsed(ctx, 2);
+}
+
+int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_dev, double rtol, double atol, int max_it, int pc, int zero_guess,
+                    int* its_out, double* rnorm_out, double* r0norm_out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "tfqmr: call build_pattern and assemble a Jacobian first");
+  NS_REQUIRE(ctx, b_owned_dev && x_local_dev, "tfqmr: NULL argument");
+  NS_REQUIRE(ctx, max_it >= 0 && rtol >= 0.0 && atol >= 0.0, "tfqmr: negative tolerance or iteration limit");
+  return tfqmr_impl(ctx, b_owned_dev, x_local_dev, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
+}
+
+int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double rtol, double atol, int max_it, int pc, int zero_guess,
+                int* its_out, double* rnorm_out, double* r0norm_out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "tfqmr: call build_pattern and assemble a Jacobian first");
+  NS_REQUIRE(ctx, b_owned && x_owned, "tfqmr: NULL argument");
+  NS_REQUIRE(ctx, max_it >= 0 && rtol >= 0.0 && atol >= 0.0, "tfqmr: negative tolerance or iteration limit");
+  cudaStream_t s = ctx->stream;
+  // d_F holds b, d_xvec the iterate (both n_cols long)
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_F, b_owned, sizeof(double) * ctx->n_owned, cudaMemcpyHostToDevice, s));
+  NS_CUDA(ctx, cudaMemsetAsync(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols, s));
+  if (!zero_guess) NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_owned, sizeof(double) * ctx->n_owned, cudaMemcpyHostToDevice, s));
+  int rc = tfqmr_impl(ctx, ctx->d_F, ctx->d_xvec, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
+  if (rc != NSGPU_OK) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(x_owned, ctx->d_xvec, sizeof(double) * ctx->n_owned, cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return NSGPU_OK;
+}
+
+int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, x_dev && y_dev, "axpy: NULL argument");
+  return axpy_impl(ctx, a, x_dev, y_dev);
+}
+
+int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, x_dev && out, "norm: NULL argument");
+  return norm_impl(ctx, x_dev, out);
 }
 
 int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
