@@ -204,6 +204,14 @@ static void launch_generic(nsgpu_ctx* ctx, const double* d_xin, bool want_J, boo
   ctx->launches += 1;
 }
 
+// assemble_matrix's BC diagonal pass on the owned rows (also used by the streamed host path)
+int k_bc_diagonal_launch(nsgpu_ctx* ctx) {
+  k_bc_diagonal<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, ctx->stream>>>(ctx->n_owned, ctx->d_bc_mult, ctx->d_diag, ctx->d_vals);
+  ctx->launches += 1;
+  NS_CUDA(ctx, cudaGetLastError());
+  return NSGPU_OK;
+}
+
 // d_xin: n_cols state (halo already refreshed).  d_Fout: n_cols residual (zeroed here; owned part meaningful).
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   cudaStream_t s = ctx->stream;

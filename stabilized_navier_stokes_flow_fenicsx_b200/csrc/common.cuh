@@ -92,6 +92,7 @@ struct nsgpu_ctx {
   int n_sms = 148;     // SM count of the device (nsgpu_create)
   int ws = 0;          // row-owner kernel: warp-specialised variant (compute warpgroups + helper warpgroup)
   int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
+  int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
   int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)
   int debug = 0;       // timing experiments only (bit 0: skip the gather phase, bit 1: skip the element algebra)
   int lanes = 1;       // lanes per incidence in the row-owner kernel: 1 (p1tet_rowslab) or 4 (p1tet_quad)
@@ -143,6 +144,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // implemented in pattern.cu / assemble.cu / spmv.cu / halo.cu
 int build_pattern_impl(nsgpu_ctx* ctx);
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);
+int k_bc_diagonal_launch(nsgpu_ctx* ctx);
 int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y);
 int halo_forward(nsgpu_ctx* ctx, double* d_v);
 int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);

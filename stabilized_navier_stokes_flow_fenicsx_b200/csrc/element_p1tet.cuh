@@ -553,6 +553,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx);
 void p1tet_free(nsgpu_ctx* ctx);
 void p1tet_mark_bc_dirty(nsgpu_ctx* ctx);
 int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y);
+int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host);
 #endif
 
 }  // namespace nsgpu

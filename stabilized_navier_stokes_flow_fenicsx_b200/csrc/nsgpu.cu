@@ -297,6 +297,17 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
   if (rc) return rc;
   NS_REQUIRE(ctx, x_local != nullptr, "x_local is NULL");
   cudaStream_t s = ctx->stream;
+  if (F_local && ctx->stream_host) {
+    // single rank, factorised kernel: H2D of x, the tile chunks and D2H of F overlap on three streams (p1tet.cu)
+    rc = p1tet_assemble_streamed(ctx, x_local, F_local);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      if (ctx->has_bc && (rc = k_bc_diagonal_launch(ctx))) return rc;
+      if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+      NS_CUDA(ctx, cudaStreamSynchronize(s));
+      return elapsed(ctx, 0);
+    }
+  }
   NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   // the Jacobian is always assembled; vals == NULL keeps it on the device (MatShell use with nsgpu_spmv)
@@ -477,6 +488,8 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->threads = (int)value;
   } else if (!strcmp(name, "ws")) {
     ctx->ws = value != 0;
+  } else if (!strcmp(name, "stream_host")) {
+    ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {
     ctx->pipe = value != 0;
   } else if (!strcmp(name, "persistent")) {

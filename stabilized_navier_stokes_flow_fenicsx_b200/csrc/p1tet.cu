@@ -20,6 +20,7 @@
 //
 // The plan (incidence lists, tiles, gather lists, output positions) is built once per pattern, on the
 // device, from the entity-level pair list the pattern builder already sorted.
+#include <algorithm>
 #include <cstdio>
 #include <vector>
 #include <cstdlib>
@@ -47,6 +48,11 @@ struct nsgpu_p1tet_plan {
   int2* d_tile_vlist = nullptr;     // [n_tiles][PIPE_VCAP] distinct vertices of the tile: (geometry vertex, first dof)
   uint32_t* d_inc_loc = nullptr;    // [n_tiles * cap] the incidence's four vertices as positions in that list (one byte each, row vertex first)
   int max_nv = 0;                   // most distinct vertices in one tile
+  // streamed host path (p1tet_assemble_streamed): tile chunks with the residual range each one finishes and the state prefix it needs
+  int n_chunks = 0;                 // 0: not built yet, -1: numbering does not allow it
+  std::vector<int64_t> chunk_tile, chunk_flo, chunk_xhi;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_h2d, ev_k;
   uint32_t* d_src = nullptr;        // gather lists, 4 bytes per incidence: (incidence-within-vertex << 2 | block), grouped by slot
   // per vertex (entity), compact
   int2* d_ent_rel = nullptr;        // (incidence offset, slot offset) relative to the tile start
@@ -629,7 +635,8 @@ template <bool WANT_J> struct PipeSmem {
 };
 
 template <bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int2* __restrict__ tile_vlist, const uint32_t* __restrict__ inc_loc) {
+__global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int2* __restrict__ tile_vlist, const uint32_t* __restrict__ inc_loc,
+                                                       const int64_t tile0) {   // this launch covers n_tiles tiles starting at tile0
   constexpr int CAP = 128;
   using View = TileView<CAP, WANT_J, PIPE_ECAP>;
   using PS = PipeSmem<WANT_J>;
@@ -644,7 +651,7 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
   auto r_loc = [&](int s) { return reinterpret_cast<uint32_t*>(ring + s * PS::ring + PIPE_VCAP * sizeof(int2)); };
   auto r_cm = [&](int s) { return r_loc(s) + CAP; };
   auto fetch_idx = [&](const int j) {
-    const int64_t t = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+    const int64_t t = tile0 + (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
     const int s = j % 3;
     cp_async8(r_vl(s) + tid, tile_vlist + t * PIPE_VCAP + tid);
     cp_async4(r_loc(s) + tid, inc_loc + t * CAP + tid);
@@ -673,7 +680,7 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
   cp_async_wait_all();
   __syncthreads();
   for (int j = 0; j < nj; ++j) {
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+    const int64_t tile = tile0 + (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
     const int s = j % 3;
     const TileHdr h = r_hdr[s];
     const uint32_t loc = r_loc(s)[tid];
@@ -943,6 +950,10 @@ void p1tet_free(nsgpu_ctx* ctx) {
   if (!P) return;
   cudaFree(P->d_tile_vlist); cudaFree(P->d_inc_loc); cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
   cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
+  if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
+  if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
+  for (cudaEvent_t e : P->ev_h2d) cudaEventDestroy(e);
+  for (cudaEvent_t e : P->ev_k) cudaEventDestroy(e);
   delete P;
   ctx->p1plan = nullptr;
 }
@@ -1195,6 +1206,43 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
 #undef PL_SCAN
 }
 
+static bool pipe_applies(nsgpu_ctx* ctx) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  return P && ctx->pipe && !ctx->ws && ctx->lanes == 1 && P->cap == 128 && P->contiguous && P->max_nent <= PIPE_ECAP && P->max_nv <= PIPE_VCAP &&
+         P->d_tile_vlist;
+}
+
+// software-pipelined persistent kernel, 2 CTAs/SM, over the tiles [t0, t1)
+static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  cudaStream_t s = ctx->stream;
+  static int pipe_occ = 0;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2)
+  if (!pipe_occ) {
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<false>::bytes));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int occ = 0;
+    NS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p1tet_pipe<true, true>, 128, PipeSmem<true>::bytes));
+    pipe_occ = occ > 0 ? (occ > 2 ? 2 : occ) : 1;
+    if (getenv("NSGPU_VERBOSE")) fprintf(stderr, "[nsgpu] k_p1tet_pipe: %zu B smem, %d CTA/SM\n", PipeSmem<true>::bytes, occ);
+  }
+  const int64_t nt = t1 - t0;
+  if (nt <= 0) return NSGPU_OK;
+  const int64_t resident = (int64_t)pipe_occ * ctx->n_sms;
+  const unsigned grid = (unsigned)(resident < nt ? resident : nt);
+#define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
+                     P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
+                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, nt, P->d_tile_vlist, P->d_inc_loc, t0
+  if (want_J && want_F) k_p1tet_pipe<true, true><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
+  else if (want_J) k_p1tet_pipe<true, false><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
+  else k_p1tet_pipe<false, true><<<grid, 128, PipeSmem<false>::bytes, s>>>(P1_PIPE_ARGS);
+#undef P1_PIPE_ARGS
+  return NSGPU_OK;
+}
+
 int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) { set_error(ctx, "p1tet plan missing"); return NSGPU_EINVAL; }
@@ -1206,30 +1254,9 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
     ctx->launches += 1;
   }
   const int lanes = ctx->lanes, cap = P->cap;
-  if (ctx->pipe && !ctx->ws && lanes == 1 && cap == 128 && P->contiguous && P->max_nent <= PIPE_ECAP && P->max_nv <= PIPE_VCAP && P->d_tile_vlist) {
-    // software-pipelined persistent kernel, 2 CTAs/SM
-    static int pipe_occ = 0;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2)
-    if (!pipe_occ) {
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<false>::bytes));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      int occ = 0;
-      NS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p1tet_pipe<true, true>, 128, PipeSmem<true>::bytes));
-      pipe_occ = occ > 0 ? (occ > 2 ? 2 : occ) : 1;
-      if (getenv("NSGPU_VERBOSE")) fprintf(stderr, "[nsgpu] k_p1tet_pipe: %zu B smem, %d CTA/SM\n", PipeSmem<true>::bytes, occ);
-    }
-    const int64_t resident = (int64_t)pipe_occ * ctx->n_sms;
-    const unsigned grid = (unsigned)(resident < P->n_tiles ? resident : P->n_tiles);
-#define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
-                     P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
-                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles, P->d_tile_vlist, P->d_inc_loc
-    if (want_J && want_F) k_p1tet_pipe<true, true><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
-    else if (want_J) k_p1tet_pipe<true, false><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
-    else k_p1tet_pipe<false, true><<<grid, 128, PipeSmem<false>::bytes, s>>>(P1_PIPE_ARGS);
-#undef P1_PIPE_ARGS
+  if (pipe_applies(ctx)) {
+    int rc = pipe_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
+    if (rc != NSGPU_OK) return rc;
     ctx->launches += 1;
     NS_CUDA(ctx, cudaGetLastError());
     return NSGPU_OK;
@@ -1272,6 +1299,131 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
   return NSGPU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ streamed host path
+// NonlinearPDE_SNESProblem.F + .J with HOST vectors (what the SNES callbacks hand over): instead of
+// "copy x in, assemble, copy F out", the tile range is cut into chunks and three streams overlap
+//   H2D: the prefix of x that chunk c needs      |  kernel: tiles of chunk c  |  D2H: the residual rows chunk c finished.
+// Tiles hold consecutive vertices, so with vertex-contiguous dofs a chunk finishes a contiguous range of F, and the state
+// it reads (its vertices and their neighbours) lies below a bound that grows with the chunk on banded numberings; on a
+// numbering without that property the first chunk simply waits for all of x (no overlap, same result).
+__global__ void k_tile_ranges(int64_t n_tiles, const TileHdr* __restrict__ hdr, const int2* __restrict__ vlist, const int32_t* __restrict__ rowdof,
+                              int2* out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const TileHdr h = hdr[t];
+  int hi = 0;
+  for (int i = 0; i < h.nv && i < PIPE_VCAP; ++i) hi = max(hi, vlist[t * PIPE_VCAP + i].y + 4);
+  out[t] = make_int2(h.nent > 0 ? rowdof[4 * h.e0] : -1, hi);
+}
+
+constexpr int STREAM_CHUNKS = 8;
+
+static int stream_plan(nsgpu_ctx* ctx) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  if (P->n_chunks != 0) return NSGPU_OK;
+  P->n_chunks = -1;
+  if (!pipe_applies(ctx) || ctx->nranks != 1 || P->n_tiles < 4 * STREAM_CHUNKS) return NSGPU_OK;
+  int2* d_rng = nullptr;
+  NS_CUDA(ctx, cudaMalloc(&d_rng, sizeof(int2) * (size_t)P->n_tiles));
+  k_tile_ranges<<<g256(P->n_tiles), 256, 0, ctx->stream>>>(P->n_tiles, P->d_tile_hdr, P->d_tile_vlist, P->d_rowdof, d_rng);
+  std::vector<int2> rng((size_t)P->n_tiles);
+  cudaError_t e = cudaMemcpyAsync(rng.data(), d_rng, sizeof(int2) * (size_t)P->n_tiles, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_rng);
+  ctx->launches += 1;
+  if (e != cudaSuccess) { set_error(ctx, std::string("stream plan: ") + cudaGetErrorString(e)); return NSGPU_ECUDA; }
+  // residual rows must come out in tile order (vertex-contiguous, increasing first dofs)
+  int prev = -1;
+  for (int64_t t = 0; t < P->n_tiles; ++t) {
+    if (rng[t].x < 0) continue;
+    if (rng[t].x <= prev) return NSGPU_OK;
+    prev = rng[t].x;
+  }
+  const int K = STREAM_CHUNKS;
+  P->chunk_tile.assign(K + 1, 0); P->chunk_flo.assign(K + 1, 0); P->chunk_xhi.assign(K, 0);
+  for (int c = 0; c <= K; ++c) P->chunk_tile[c] = P->n_tiles * c / K;
+  int64_t xhi = 0;
+  for (int c = 0; c < K; ++c) {
+    int64_t t = P->chunk_tile[c];
+    while (t < P->n_tiles && rng[t].x < 0) ++t;
+    P->chunk_flo[c] = c == 0 ? 0 : (t < P->n_tiles ? rng[t].x : ctx->n_dofs);
+    for (int64_t u = P->chunk_tile[c]; u < P->chunk_tile[c + 1]; ++u) xhi = std::max<int64_t>(xhi, rng[u].y);
+    P->chunk_xhi[c] = std::min<int64_t>(xhi, ctx->n_dofs);
+  }
+  P->chunk_flo[K] = ctx->n_dofs;
+  P->chunk_xhi[K - 1] = ctx->n_dofs;
+  NS_CUDA(ctx, cudaStreamCreateWithFlags(&P->s_h2d, cudaStreamNonBlocking));
+  NS_CUDA(ctx, cudaStreamCreateWithFlags(&P->s_d2h, cudaStreamNonBlocking));
+  P->ev_h2d.resize(K); P->ev_k.resize(K);
+  for (int c = 0; c < K; ++c) {
+    NS_CUDA(ctx, cudaEventCreateWithFlags(&P->ev_h2d[c], cudaEventDisableTiming));
+    NS_CUDA(ctx, cudaEventCreateWithFlags(&P->ev_k[c], cudaEventDisableTiming));
+  }
+  P->n_chunks = K;
+  return NSGPU_OK;
+}
+
+__global__ void k_set_bc_range(int64_t lo, int64_t hi, const uint8_t* __restrict__ marker, const double* __restrict__ value,
+                               const double* __restrict__ xv, double* F) {
+  const int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < hi && marker[i]) F[i] = xv[i] - value[i];
+}
+
+// returns 1 when the streamed path ran (J resident in ctx->d_vals, F in F_host and ctx->d_F), 0 when it does not apply
+int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host) {
+  if (ctx->nranks != 1 || ctx->gdim != 3 || ctx->vdeg != 1 || ctx->form.flavour != NSGPU_FORM_GMETRIC || ctx->kernel_sel == NSGPU_KERNEL_GENERIC ||
+      !ctx->extra_rows.empty() || ctx->debug)
+    return 0;
+  if (!p1tet_fast_available(ctx) || !pipe_applies(ctx)) return 0;
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  if (stream_plan(ctx) != NSGPU_OK || P->n_chunks <= 0) return 0;
+  cudaStream_t s = ctx->stream;
+#define ST_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) { set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e__)); return NSGPU_ECUDA; } \
+  } while (0)
+  if (P->bc_dirty) {
+    k_inc_bc<<<g256(P->n_tiles * P->cap), 256, 0, s>>>(P->n_tiles * P->cap, P->d_inc_cell, ctx->d_dofmap, ctx->has_bc ? ctx->d_bc_marker : nullptr);
+    P->bc_dirty = false;
+    ctx->launches += 1;
+  }
+  const int K = P->n_chunks;
+  // the copy streams must not overtake work still queued on the compute stream (previous users of d_xvec / d_F)
+  ST_CUDA(cudaEventRecord(ctx->ev[0], s));
+  ST_CUDA(cudaStreamWaitEvent(P->s_h2d, ctx->ev[0], 0));
+  ST_CUDA(cudaStreamWaitEvent(P->s_d2h, ctx->ev[0], 0));
+  int64_t covered = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t hi = P->chunk_xhi[c];
+    if (hi > covered) {
+      ST_CUDA(cudaMemcpyAsync(ctx->d_xvec + covered, x_host + covered, sizeof(double) * (size_t)(hi - covered), cudaMemcpyHostToDevice, P->s_h2d));
+      covered = hi;
+    }
+    ST_CUDA(cudaEventRecord(P->ev_h2d[c], P->s_h2d));
+  }
+  for (int c = 0; c < K; ++c) {
+    ST_CUDA(cudaStreamWaitEvent(s, P->ev_h2d[c], 0));
+    int rc = pipe_launch(ctx, ctx->d_xvec, true, true, ctx->d_F, P->chunk_tile[c], P->chunk_tile[c + 1]);
+    if (rc != NSGPU_OK) return rc;
+    const int64_t lo = P->chunk_flo[c], hi = P->chunk_flo[c + 1];
+    if (ctx->has_bc && hi > lo) {   // set_bc(F, bc, x, -1.0) on the rows this chunk finished
+      k_set_bc_range<<<g256(hi - lo), 256, 0, s>>>(lo, hi, ctx->d_bc_marker, ctx->d_bc_value, ctx->d_xvec, ctx->d_F);
+      ctx->launches += 1;
+    }
+    ctx->launches += 1;
+    ST_CUDA(cudaEventRecord(P->ev_k[c], s));
+    ST_CUDA(cudaStreamWaitEvent(P->s_d2h, P->ev_k[c], 0));
+    if (hi > lo) ST_CUDA(cudaMemcpyAsync(F_host + lo, ctx->d_F + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyDeviceToHost, P->s_d2h));
+  }
+  ST_CUDA(cudaEventRecord(ctx->ev[1], s));
+  ST_CUDA(cudaGetLastError());
+  ST_CUDA(cudaStreamSynchronize(P->s_d2h));
+#undef ST_CUDA
+  return 1;
 }
 
 }  // namespace nsgpu

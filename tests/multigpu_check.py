@@ -62,7 +62,14 @@ def main():
         y = asm.mult(xl)
         ey = np.abs(y - (A @ xv)[l2g[:n_owned]]).max()
         assert ey <= 1e-12 * np.abs(A @ xv).max(), f"rank {rank} kernel {kernel}: MatMult err {ey}"
-        print(f"rank {rank}/{size} kernel {kernel}: J {worst:.2e} F {eF:.2e} Jx {ey:.2e} (n_owned {n_owned}, ghosts {part.n_ghost}, col ghosts {asm.n_cols - n_dofs})", flush=True)
+        # KSPTFQMR on the distributed Jacobian (dot products over ncclAllReduce) against a serial direct solve
+        import scipy.sparse.linalg as spla
+        x_ref = spla.spsolve(A.tocsc(), gF)
+        xs, info = asm.tfqmr(F[:n_owned], rtol=1e-12, max_it=4000, pc=4)
+        ex = np.abs(xs - x_ref[l2g[:n_owned]]).max()
+        assert ex <= 1e-8 * np.abs(x_ref).max(), f"rank {rank} kernel {kernel}: TFQMR err {ex} {info}"
+        print(f"rank {rank}/{size} kernel {kernel}: J {worst:.2e} F {eF:.2e} Jx {ey:.2e} tfqmr {ex:.2e} in {info['its']} its "
+              f"(n_owned {n_owned}, ghosts {part.n_ghost}, col ghosts {asm.n_cols - n_dofs})", flush=True)
         asm.close()
     comm.close()
 
