@@ -306,10 +306,13 @@ class NonlinearPDE_SNESProblem:
     a Vec is accessed through ``.array``; a Mat is filled with ``setValuesCSR`` when it has that method,
     otherwise ``J`` is treated as the CSR value array itself."""
 
-    def __init__(self, assembler, u=None):
+    def __init__(self, assembler, u=None, fuse=True):
         self.asm = assembler
         self.u = u                       # optional mirror of the state vector (self.u of the reference)
         self.pattern = None
+        # SNES evaluates F and then J at the same iterate: with fuse the residual call assembles the Jacobian in the same
+        # pass (it stays on the device) and the Jacobian call that follows recognises the state and reuses it.
+        self.asm.set_option("fuse_fj", 1 if fuse else 0)
 
     def create_matrix(self):
         self.pattern = self.asm.create_matrix()

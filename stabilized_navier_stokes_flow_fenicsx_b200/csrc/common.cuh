@@ -92,6 +92,10 @@ struct nsgpu_ctx {
   int n_sms = 148;     // SM count of the device (nsgpu_create)
   int ws = 0;          // row-owner kernel: warp-specialised variant (compute warpgroups + helper warpgroup)
   int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
+  int fuse_fj = 0;     // nsgpu_residual also assembles J (one pass) and nsgpu_jacobian reuses it when called with the same state
+  bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
+  double* d_x_last = nullptr;
+  int64_t fused_hits = 0;
   int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
   int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)
   int debug = 0;       // timing experiments only (bit 0: skip the gather phase, bit 1: skip the element algebra)

@@ -33,6 +33,38 @@ static int elapsed(nsgpu_ctx* ctx, int slot) {
   return NSGPU_OK;
 }
 
+namespace nsgpu {
+// "SNES evaluates F and then J at the same iterate": with option fuse_fj the residual call assembles the Jacobian in the
+// same pass and remembers the state it was linearised at; the Jacobian call that follows only has to recognise that state.
+__global__ void k_differs(int64_t n, const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, int* flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && a[i] != b[i]) *flag = 1;
+}
+
+static int remember_state(nsgpu_ctx* ctx) {
+  if (!ctx->d_x_last) NS_CUDA(ctx, cudaMalloc(&ctx->d_x_last, sizeof(double) * (size_t)(ctx->n_cols > 0 ? ctx->n_cols : 1) + sizeof(int)));
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_x_last, ctx->d_xvec, sizeof(double) * (size_t)ctx->n_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->jac_valid = true;
+  return NSGPU_OK;
+}
+
+// is the Jacobian resident in d_vals the one of the state now in d_xvec?  (bitwise comparison on the device)
+static int same_state(nsgpu_ctx* ctx, bool* same) {
+  *same = false;
+  if (!ctx->jac_valid || !ctx->d_x_last) return NSGPU_OK;
+  int* d_flag = reinterpret_cast<int*>(ctx->d_x_last + (ctx->n_cols > 0 ? ctx->n_cols : 1));
+  NS_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+  k_differs<<<(unsigned)ceil_div(ctx->n_dofs > 0 ? ctx->n_dofs : 1, 256), 256, 0, ctx->stream>>>(
+      ctx->n_dofs, reinterpret_cast<const unsigned long long*>(ctx->d_xvec), reinterpret_cast<const unsigned long long*>(ctx->d_x_last), d_flag);
+  ctx->launches += 1;
+  int flag = 1;
+  NS_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *same = flag == 0;
+  return NSGPU_OK;
+}
+}  // namespace nsgpu
+
 extern "C" {
 
 int nsgpu_version(void) { return 100; }
@@ -74,6 +106,7 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
   krylov_free(ctx);
+  cudaFree(ctx->d_x_last);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   if (ctx->tev[0]) cudaEventDestroy(ctx->tev[0]);
@@ -115,6 +148,7 @@ int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_d
   ctx->vdeg = vdeg; ctx->nd = gd * nvn + gd + 1; ctx->nent = nvn;
   ctx->n_owned = n_dofs_owned; ctx->n_ghost = n_dofs_ghost; ctx->n_dofs = n_dofs_owned + n_dofs_ghost;
   ctx->n_cols = ctx->n_dofs;
+  cudaFree(ctx->d_x_last); ctx->d_x_last = nullptr; ctx->jac_valid = false;
   ctx->colx_leader.clear(); ctx->colx_slot.clear(); ctx->colx_size.clear();
   ctx->extra_rows.clear(); ctx->extra_cols.clear();
   ctx->pattern_built = false;
@@ -135,6 +169,7 @@ int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_d
 }
 
 int nsgpu_set_form(nsgpu_ctx* ctx, int flavour, double nu, double Ci, double alpha, double sp, double beta) {
+  if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, flavour >= 0 && flavour <= 2, "set_form: unknown flavour");
   NS_REQUIRE(ctx, flavour == NSGPU_FORM_STOKES || nu > 0.0, "set_form: nu must be positive");
@@ -144,6 +179,7 @@ int nsgpu_set_form(nsgpu_ctx* ctx, int flavour, double nu, double Ci, double alp
 }
 
 int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr, const int32_t* bc_dofs, const double* bc_vals) {
+  if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->n_dofs > 0, "set_bcs: call set_space first");
   NS_REQUIRE(ctx, n_bc >= 0 && (n_bc == 0 || (bc_ptr && bc_dofs && bc_vals)), "set_bcs: NULL arrays");
@@ -192,6 +228,7 @@ int nsgpu_set_col_ghosts(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_
                         size[k] >= 1 && size[k] <= KMAX, "set_col_ghosts: bad entity description");
   }
   ctx->n_cols = ctx->n_dofs + n_extra;
+  cudaFree(ctx->d_x_last); ctx->d_x_last = nullptr; ctx->jac_valid = false;
   ctx->colx_leader.assign(leader_local, leader_local + n_extra);
   ctx->colx_slot.assign(slot, slot + n_extra);
   ctx->colx_size.assign(size, size + n_extra);
@@ -234,6 +271,7 @@ int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* star
 }
 
 int nsgpu_build_pattern(nsgpu_ctx* ctx, int64_t* nnz_out) {
+  if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->d_dofmap != nullptr, "build_pattern: call set_mesh and set_space first");
   cudaEvent_t a, b;
@@ -304,6 +342,7 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
     if (rc == 1) {
       if (ctx->has_bc && (rc = k_bc_diagonal_launch(ctx))) return rc;
       if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+      if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
       NS_CUDA(ctx, cudaStreamSynchronize(s));
       return elapsed(ctx, 0);
     }
@@ -316,6 +355,7 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
   if ((rc = assemble_impl(ctx, ctx->d_xvec, want_J, want_F, ctx->d_F))) return rc;
   if (want_F) NS_CUDA(ctx, cudaMemcpyAsync(F_local, ctx->d_F, sizeof(double) * ctx->n_dofs, cudaMemcpyDeviceToHost, s));
   if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return elapsed(ctx, 0);
 }
@@ -325,6 +365,7 @@ int nsgpu_residual(nsgpu_ctx* ctx, const double* x_local, double* F_local) {
   int rc = ready(ctx);
   if (rc) return rc;
   NS_REQUIRE(ctx, x_local && F_local, "residual: NULL argument");
+  if (ctx->fuse_fj) return nsgpu_jacobian_residual(ctx, x_local, nullptr, F_local);   // J stays resident for the nsgpu_jacobian call that follows
   cudaStream_t s = ctx->stream;
   NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
@@ -342,8 +383,17 @@ int nsgpu_jacobian(nsgpu_ctx* ctx, const double* x_local, double* vals) {
   cudaStream_t s = ctx->stream;
   NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  bool same = false;
+  if (ctx->fuse_fj && (rc = same_state(ctx, &same))) return rc;
+  if (same) {   // assembled by the residual call at this very state
+    ctx->fused_hits += 1;
+    if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+    NS_CUDA(ctx, cudaStreamSynchronize(s));
+    return NSGPU_OK;
+  }
   if ((rc = assemble_impl(ctx, ctx->d_xvec, true, false, ctx->d_F))) return rc;
   if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return elapsed(ctx, 0);
 }
@@ -411,6 +461,7 @@ int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out) {
 }
 
 int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
+  if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built && vals, "set_values: no pattern or NULL values");
   NS_CUDA(ctx, cudaMemcpy(ctx->d_vals, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
@@ -477,6 +528,7 @@ int nsgpu_host_alloc_pinned(int64_t bytes, void** out) {
 int nsgpu_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? NSGPU_OK : NSGPU_ECUDA; }
 
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
+  if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, name != nullptr, "set_option: NULL name");
   if (!strcmp(name, "kernel")) {
@@ -488,6 +540,8 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->threads = (int)value;
   } else if (!strcmp(name, "ws")) {
     ctx->ws = value != 0;
+  } else if (!strcmp(name, "fuse_fj")) {
+    ctx->fuse_fj = value != 0;
   } else if (!strcmp(name, "stream_host")) {
     ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {

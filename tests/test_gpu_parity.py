@@ -204,6 +204,35 @@ def test_size_independent_properties_at_scale():
     asm.close()
 
 
+def test_fused_F_then_J_reuses_the_jacobian(oracle):
+    """Option fuse_fj (what NonlinearPDE_SNESProblem switches on): nsgpu_residual assembles J in the same pass and the
+    nsgpu_jacobian call that follows at the same state returns it; a different state, form or BC set re-assembles."""
+    m, sp, w, bcs, fk = _case("duct_p1")
+    indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix(fetch=False)
+    v_plain = asm.jacobian(w)
+    asm.set_option("fuse_fj", 1)
+    launches = asm.launch_count()
+    gF = asm.residual(w)
+    n_fused = asm.launch_count() - launches
+    gv = asm.jacobian(w)                                   # same state: served from the resident values
+    n_reuse = asm.launch_count() - launches - n_fused
+    assert n_reuse <= 1, n_reuse                           # only the state comparison kernel
+    np.testing.assert_array_equal(gv, v_plain)
+    assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    w2 = w.copy(); w2[sp.n_dofs // 2] += 1e-3
+    gv2 = asm.jacobian(w2)                                 # different state: assembled
+    assert np.abs(gv2 - v_plain).max() > 0
+    asm.set_option("fuse_fj", 0); ref2 = asm.jacobian(w2); asm.set_option("fuse_fj", 1)
+    np.testing.assert_array_equal(gv2, ref2)
+    asm.residual(w)
+    asm.set_form(flavour=0, nu=0.05)                       # form changed after F: the resident J is stale
+    gv3 = asm.jacobian(w)
+    assert np.abs(gv3 - v_plain).max() > 0
+    asm.close()
+
+
 def test_streamed_host_path_is_bitwise_identical():
     """nsgpu_jacobian_residual with host vectors overlaps H2D(x) / tile chunks / D2H(F) on three streams when the pipelined
     kernel applies; it must give exactly what the plain copy-assemble-copy sequence gives (also after a BC / form change)."""
