@@ -19,6 +19,10 @@ struct PointData {
   double u[GD], gu[GD][GD], p, gp[GD], divu, conv[GD];
   double tau, nuL, dtau[GD], dnuL[GD], rM[GD];
   double W;                  // quadrature weight * |det J|
+  // d rM_j / d u_(n,d): derivative of the strong momentum residual w.r.t. velocity dof (node n, component d) -- independent
+  // of the test row, so it is tabulated once per point instead of being rebuilt for each of the ND rows (NS flavours only)
+  // (P2 only: with P1 the expression has no Hessian part and is cheaper to form on the fly than to park in shared memory)
+  double drM[VDEG == 2 ? T::NVN : 1][GD][GD];
 };
 
 template <int GD>
@@ -100,6 +104,18 @@ NS_HD void point_setup(const FormParams& f, const double* x, const double* w, in
     }
     for (int j = 0; j < GD; ++j) P.rM[j] = P.conv[j] - 0.5 * f.nu * visc[j] + P.gp[j];
   }
+  // row-independent derivative table
+  if (VDEG == 2)
+  for (int n = 0; n < T::NVN; ++n) {
+    double udNn = 0.0, lap = 0.0;
+    for (int j = 0; j < GD; ++j) { udNn += P.u[j] * P.dN[n][j]; lap += vbasis_d2<GD, VDEG>(g, n, j, j); }
+    for (int d = 0; d < GD; ++d)
+      for (int j = 0; j < GD; ++j) {
+        const double h2 = (j == d ? lap : 0.0) + vbasis_d2<GD, VDEG>(g, n, j, d);
+        P.drM[n][d][j] = (f.flavour == 0) ? P.N[n] * P.gu[d][j] + P.u[d] * P.dN[n][j] - f.nu * h2
+                                          : P.N[n] * P.gu[j][d] + (j == d ? udNn : 0.0) - 0.5 * f.nu * h2;
+      }
+  }
 }
 
 // constant Hessian entries of velocity basis n from the barycentric gradients
@@ -109,6 +125,13 @@ template <int GD, int VDEG> NS_HD double d2_from_gl(const CellData<GD>& C, int n
   int a, b;
   edge_vertices<GD>(n - GD - 1, a, b);
   return 4.0 * (C.gl[a][j] * C.gl[b][k] + C.gl[b][j] * C.gl[a][k]);
+}
+
+// d rM_j / d u_(n,d) (see PointData::drM)
+template <int GD, int VDEG>
+NS_HD double drM_entry(const FormParams& f, const PointData<GD, VDEG>& P, int n, int d, int j, double udNn) {
+  if (VDEG == 2) return P.drM[n][d][j];
+  return (f.flavour == 0) ? P.N[n] * P.gu[d][j] + P.u[d] * P.dN[n][j] : P.N[n] * P.gu[j][d] + (j == d ? udNn : 0.0);
 }
 
 // stage 2: contribution of ONE quadrature point to row `row` (accumulated into Arow[ND] when WANT_A, *brow when WANT_B)
@@ -181,21 +204,14 @@ NS_HD void row_from_point(const FormParams& f, const PointData<GD, VDEG>& P, con
 #pragma unroll
       for (int n = 0; n < T::NVN; ++n) {
         const double N = P.N[n];
-        double udNn = 0.0, dNdN = 0.0, lap = 0.0;
-        for (int j = 0; j < GD; ++j) { udNn += P.u[j] * P.dN[n][j]; dNdN += P.dN[n][j] * dNm[j]; lap += d2_from_gl<GD, VDEG>(C, n, j, j); }
+        double udNn = 0.0, dNdN = 0.0;
+        for (int j = 0; j < GD; ++j) { udNn += P.u[j] * P.dN[n][j]; dNdN += P.dN[n][j] * dNm[j]; }
 #pragma unroll
         for (int d = 0; d < GD; ++d) {
           double s = (N * P.gu[c][d] + (c == d ? udNn : 0.0)) * Nm;
           if (c == d) s += f.nu * dNdN;
           double drT = 0.0, rdT = 0.0;
-          for (int j = 0; j < GD; ++j) {
-            double drM;
-            if (f.flavour == 0)
-              drM = N * P.gu[d][j] + P.u[d] * P.dN[n][j] - f.nu * ((j == d ? lap : 0.0) + d2_from_gl<GD, VDEG>(C, n, j, d));
-            else
-              drM = N * P.gu[j][d] + (j == d ? udNn : 0.0) - 0.5 * f.nu * ((j == d ? lap : 0.0) + d2_from_gl<GD, VDEG>(C, n, j, d));
-            drT += drM * Tt[j];
-          }
+          for (int j = 0; j < GD; ++j) drT += drM_entry<GD, VDEG>(f, P, n, d, j, udNn) * Tt[j];
           if (f.flavour == 0) { if (c == d) for (int j = 0; j < GD; ++j) rdT += P.rM[j] * N * dNm[j]; }
           else rdT = P.rM[c] * N * dNm[d];
           s += P.dtau[d] * N * rT + tau * (drT + rdT);
@@ -218,19 +234,12 @@ NS_HD void row_from_point(const FormParams& f, const PointData<GD, VDEG>& P, con
 #pragma unroll
       for (int n = 0; n < T::NVN; ++n) {
         const double N = P.N[n];
-        double udNn = 0.0, lap = 0.0;
-        for (int j = 0; j < GD; ++j) { udNn += P.u[j] * P.dN[n][j]; lap += d2_from_gl<GD, VDEG>(C, n, j, j); }
+        double udNn = 0.0;
+        if (VDEG == 1) for (int j = 0; j < GD; ++j) udNn += P.u[j] * P.dN[n][j];
 #pragma unroll
         for (int d = 0; d < GD; ++d) {
           double drT = 0.0;
-          for (int j = 0; j < GD; ++j) {
-            double drM;
-            if (f.flavour == 0)
-              drM = N * P.gu[d][j] + P.u[d] * P.dN[n][j] - f.nu * ((j == d ? lap : 0.0) + d2_from_gl<GD, VDEG>(C, n, j, d));
-            else
-              drM = N * P.gu[j][d] + (j == d ? udNn : 0.0) - 0.5 * f.nu * ((j == d ? lap : 0.0) + d2_from_gl<GD, VDEG>(C, n, j, d));
-            drT += drM * dNm[j];
-          }
+          for (int j = 0; j < GD; ++j) drT += drM_entry<GD, VDEG>(f, P, n, d, j, udNn) * dNm[j];
           Arow[GD * n + d] += W * (Nm * P.dN[n][d] + P.dtau[d] * N * rT + tau * drT);
         }
       }
