@@ -30,8 +30,11 @@ WORKLOADS = {  # n_cross, n_long  
 }
 NU, CI = 0.1, 36.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the assembly kernel, one launch, from the committed ncu --set full capture
-# (default kernel options, 1 GPU).  The tile-padded incidence arrays add ~10 GB of reads to the 21.0 GB algorithmic bytes.
-NCU_TRAFFIC = {"L": (31.50e9, "profiles/r1_ncu_full_L_p1tet_v5_and_spmv.txt")}
+# (default kernel options, 1 GPU): 6.00 GB read + 16.46 GB written, against 21.0 GB algorithmic (the pipelined kernel reads
+# one vertex list per tile instead of eight indices per incidence, which removed ~9 GB of index traffic).
+NCU_TRAFFIC = {"L": (22.46e9, "profiles/r1b_ncu_full_L_p1tet_pipe.txt")}
+# executed fp64 work of the assembly kernel from the same capture: 2*DFMA + DADD + DMUL thread instructions per cell
+FLOP_PER_CELL = 5806
 
 
 def peaks():
@@ -243,6 +246,25 @@ def run_ours(args):
     e2e_ms = comm.max(1e3 * (time.perf_counter() - t0) / e2e_steps)
     f_checksum = float(np.abs(Fh[: asm.n_owned]).sum())
 
+    # what one Newton iterate costs through the SNES callbacks (F then J at the same state, host vectors), with the
+    # residual call assembling the Jacobian in the same pass (option fuse_fj) -- and the Krylov iteration on the resident J
+    asm.set_option("fuse_fj", 1)
+    asm.residual(xh, out=Fh); asm.jacobian(xh, fetch=False)
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        asm.residual(xh, out=Fh)
+        asm.jacobian(xh, fetch=False)
+    snes_ms = comm.max(1e3 * (time.perf_counter() - t0) / e2e_steps)
+    asm.set_option("fuse_fj", 0)
+    asm.jacobian_residual_dev(x_dev, True, F_dev)
+    k_its = 5
+    asm.tfqmr_dev(F_dev, y_dev, rtol=0.0, max_it=1, pc=4)          # allocate work vectors
+    asm.sync(); comm.barrier()
+    t0 = time.perf_counter()
+    kinfo = asm.tfqmr_dev(F_dev, y_dev, rtol=0.0, max_it=k_its, pc=4)
+    tfqmr_ms = comm.max(1e3 * (time.perf_counter() - t0) / max(kinfo["its"], 1))
+
     nc_total = 6 * n_cross * n_cross * n_long
     nv_total = (n_cross + 1) ** 2 * (n_long + 1)
     ndof_total = 4 * nv_total
@@ -268,10 +290,11 @@ def run_ours(args):
                          "traffic": (NCU_TRAFFIC[args.workload][0] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
                          "traffic_source": (NCU_TRAFFIC[args.workload][1] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
                          "peak_source": how, "kernel_ms": kernel_ms_avg, "algorithmic_bytes": b_jf,
-                         "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): ncu shows DRAM ~5 %, fp64 pipe ~25 % busy"},
-            "fp64": {"flop_per_cell_executed": 5600, "achieved_TFLOP/s": 5600 * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
-                     "peak_TFLOP/s": 33.9 * world, "frac": 5600 * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (33.9 * world),
-                     "source": "executed DFMA/DMUL/DADD counts from ncu (profiles/r1_ncu_full_L_p1tet_v5_and_spmv.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
+                         "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): ncu shows DRAM ~9 %, "
+                                 "fp64 pipe ~37 % busy, DRAM traffic 1.07x the algorithmic bytes"},
+            "fp64": {"flop_per_cell_executed": FLOP_PER_CELL, "achieved_TFLOP/s": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
+                     "peak_TFLOP/s": 33.9 * world, "frac": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (33.9 * world),
+                     "source": "executed DFMA/DMUL/DADD thread instructions from ncu (profiles/r1b_ncu_full_L_p1tet_pipe.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
             "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
                               "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
             "spmv": {"ms": s_ms, "GB/s": b_spmv / (s_ms * 1e-3) / 1e9, "frac": b_spmv / (s_ms * 1e-3) / 1e9 / hbm_total,
@@ -283,6 +306,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": 8 * ndof_total, "ms_per_step": e2e_ms,
                     "what": "NSAssembler.jacobian_residual(x_host_pinned) -> F_host; J stays device-resident for MatMult (MatShell mode)",
                     "F_l1_checksum": f_checksum},
+            "snes_iterate": {"ms": snes_ms, "what": "NonlinearPDE_SNESProblem-style callback pair per Newton iterate: nsgpu_residual(x_host) -> F_host "
+                                                      "then nsgpu_jacobian(x_host) (J stays resident), option fuse_fj: the residual pass assembles J, the Jacobian "
+                                                      "call recognises the state on the device and reuses it"},
+            "tfqmr": {"ms_per_iteration": tfqmr_ms, "iterations_timed": kinfo["its"], "pc": "4x4 vertex-block Jacobi",
+                      "what": "device-resident KSPTFQMR iteration on the resident Jacobian: 2 MatMult + fused vector updates / reductions; "
+                              "includes the set-up product and the true-residual check amortised over the timed iterations"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
