@@ -326,7 +326,7 @@ def run_ours(args):
 
 
 def asm_kernel_name(asm):
-    return "auto"
+    return asm.last_kernel_name()
 
 
 def main():

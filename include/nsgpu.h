@@ -157,6 +157,10 @@ int nsgpu_host_free_pinned(void* p);
  * (timing experiments only). */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
+/* Which assembly kernel variant the last residual / Jacobian call ran: "p1tet_pipe", "p1tet_pipe (streamed host vectors)",
+ * "p1tet_tiles", "p1tet_ws", "p1tet_quad", "generic_coop", "generic_row" (static string, never NULL). */
+const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx);
+
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.
  * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build. */
 int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n);

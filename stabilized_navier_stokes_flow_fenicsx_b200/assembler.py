@@ -241,6 +241,9 @@ class NSAssembler:
         keys = ["jacobian_residual", "residual", "spmv", "halo", "h2d", "d2h", "pattern", "spare"]
         return dict(zip(keys, list(ms)))
 
+    def last_kernel_name(self):
+        return self.lib.nsgpu_last_kernel_name(self.ctx).decode()
+
     def launch_count(self):
         return int(self.lib.nsgpu_launch_count(self.ctx))
 

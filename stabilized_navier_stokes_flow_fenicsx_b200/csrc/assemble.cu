@@ -235,6 +235,7 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   } else {
     const int key = ctx->gdim * 10 + ctx->vdeg;
     const bool coop = ctx->kernel_sel != NSGPU_KERNEL_GENERIC;   // AUTO: cooperative (shared point data); GENERIC: thread per row
+    ctx->last_kernel = coop ? "generic_coop" : "generic_row";
     switch (key) {
       case 31: coop ? launch_coop<3, 1>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<3, 1>(ctx, d_xin, want_J, want_F, d_Fout); break;
       case 32: coop ? launch_coop<3, 2>(ctx, d_xin, want_J, want_F, d_Fout) : launch_generic<3, 2>(ctx, d_xin, want_J, want_F, d_Fout); break;

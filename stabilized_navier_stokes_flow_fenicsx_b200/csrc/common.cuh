@@ -107,6 +107,7 @@ struct nsgpu_ctx {
   cudaEvent_t tev[2] = {nullptr, nullptr};   // user timer (nsgpu_timer_start/stop)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t launches = 0;
+  const char* last_kernel = "none";   // which assembly variant the last call used (nsgpu_last_kernel_name)
 
   // multi-GPU
   int rank = 0, nranks = 1;

@@ -527,6 +527,8 @@ int nsgpu_host_alloc_pinned(int64_t bytes, void** out) {
 
 int nsgpu_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? NSGPU_OK : NSGPU_ECUDA; }
 
+const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
   if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);

@@ -1255,6 +1255,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   }
   const int lanes = ctx->lanes, cap = P->cap;
   if (pipe_applies(ctx)) {
+    ctx->last_kernel = "p1tet_pipe";
     int rc = pipe_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
     if (rc != NSGPU_OK) return rc;
     ctx->launches += 1;
@@ -1263,6 +1264,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   }
   if (ctx->ws && want_J && lanes == 1 && cap == WS_CAP && P->max_nent <= WS_ECAP) {
     // warp-specialised persistent ring kernel: one CTA per SM
+    ctx->last_kernel = "p1tet_ws";
     constexpr size_t SMEM = WS_NBUF * WS_VIEW;
     const unsigned grid = (unsigned)(ctx->n_sms < P->n_tiles ? ctx->n_sms : P->n_tiles);
     static bool attr_set = false;
@@ -1287,6 +1289,7 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
                 reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles
   // one-thread kernels are persistent (grid = resident CTAs); the quad kernels take one tile per CTA
+  ctx->last_kernel = lanes == 4 ? "p1tet_quad" : "p1tet_tiles";
   const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 96 ? 3 : (cap == 64 ? 4 : (cap == 32 ? 8 : 1))));
   const unsigned grid = (unsigned)((lanes == 4 || ctx->persistent == 0) ? P->n_tiles : (resident < P->n_tiles ? resident : P->n_tiles));
 #define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
@@ -1392,6 +1395,7 @@ int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host
     ctx->launches += 1;
   }
   const int K = P->n_chunks;
+  ctx->last_kernel = "p1tet_pipe (streamed host vectors)";
   // the copy streams must not overtake work still queued on the compute stream (previous users of d_xvec / d_F)
   ST_CUDA(cudaEventRecord(ctx->ev[0], s));
   ST_CUDA(cudaStreamWaitEvent(P->s_h2d, ctx->ev[0], 0));

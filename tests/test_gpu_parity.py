@@ -144,6 +144,51 @@ def test_arbitrary_dof_numbering(oracle):
     asm.close()
 
 
+def test_irregular_mesh_vertex_blocked_numbering(oracle):
+    """An unstructured-looking mesh with dolfinx-like vertex-blocked dofs: vertices renumbered at random (so a tile's
+    vertices and their neighbours are scattered over the whole index range), coordinates jittered, cells shuffled and their
+    local vertex order rotated.  The factorised / pipelined kernel must still apply (kernel=2 fails loudly otherwise) and
+    agree with the oracle -- through the device entry point and through the streamed host-vector path."""
+    rng = np.random.default_rng(11)
+    m0 = M.duct_mesh(8, 24)
+    nv = m0.x.shape[0]
+    vperm = rng.permutation(nv).astype(np.int32)          # old vertex -> new vertex
+    x = np.empty_like(m0.x); x[vperm] = m0.x + 0.02 * rng.standard_normal(m0.x.shape) * (4.0 / 24)
+    cells = vperm[m0.cells]
+    cells = cells[rng.permutation(cells.shape[0])]
+    rot = rng.integers(0, 4, size=cells.shape[0])
+    cells = np.take_along_axis(cells, (np.arange(4)[None, :] + rot[:, None]) % 4, axis=1).astype(np.int32)
+    # keep the orientation handling honest: swap two vertices in a third of the cells (negative Jacobians)
+    flip = rng.random(cells.shape[0]) < 0.33
+    cells[flip, 0], cells[flip, 1] = cells[flip, 1].copy(), cells[flip, 0].copy()
+    dofmap = np.concatenate([(4 * cells[:, :, None] + np.arange(3)[None, None, :]).reshape(len(cells), 12), 4 * cells + 3], axis=1).astype(np.int32)
+    n = 4 * nv
+    w = 0.3 * rng.standard_normal(n)
+    wall = np.flatnonzero((np.abs(np.abs(x[:, 1]) - 0.5) < 0.03) | (np.abs(np.abs(x[:, 2]) - 0.5) < 0.03))
+    bcs = [((4 * wall[:, None] + np.arange(3)[None, :]).ravel().astype(np.int32), 0.0),
+           ((4 * np.flatnonzero(x[:, 0] > 3.9) + 3).astype(np.int32), 0.0)]
+    form = oracle.Form(gdim=3, vdeg=1, flavour=0, nu=0.05)
+    marker, value, mult = oracle.bc_arrays(n, [b[0] for b in bcs], [np.broadcast_to(b[1], (len(b[0]),)) for b in bcs])
+    indptr, indices = oracle.build_pattern(dofmap, n)
+    vals = oracle.assemble_jacobian(form, x, cells, dofmap, w, indptr, indices, marker, mult)
+    F = oracle.assemble_residual(form, x, cells, dofmap, w, marker, value)
+    oracle.set_bc(F, [b[0] for b in bcs], [np.broadcast_to(b[1], (len(b[0]),)) for b in bcs], w)
+    asm = NSAssembler(x, cells, dofmap, vdeg=1)
+    asm.set_form(flavour=0, nu=0.05); asm.set_bcs(bcs)
+    asm.set_option("kernel", 2)
+    gp, gi = asm.create_matrix()
+    np.testing.assert_array_equal(gp, indptr); np.testing.assert_array_equal(gi, indices)
+    for stream_host in (1, 0):
+        asm.set_option("stream_host", stream_host)
+        gv, gF = asm.jacobian_residual(w)
+        assert asm.last_kernel_name() == ("p1tet_pipe (streamed host vectors)" if stream_host else "p1tet_pipe")
+        assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+        assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    xv = rng.standard_normal(n)
+    assert np.abs(asm.mult(xv) - oracle.spmv(indptr, indices, vals, xv)).max() <= RTOL * np.abs(vals).max() * np.abs(xv).max() * 60
+    asm.close()
+
+
 def test_reynolds_sweep_without_rebuild(oracle):
     """run_all_RE.sh sweeps Re on one mesh: set_form may change nu without touching the pattern."""
     m, sp, w, bcs, fk = _case("duct_p1_re70")
