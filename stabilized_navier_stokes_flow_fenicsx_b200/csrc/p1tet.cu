@@ -223,6 +223,49 @@ __global__ void k_tile_pack(int cap, const int64_t* __restrict__ tile_ent, const
   }
 }
 
+// Order each slot's gather list so that the eight lanes of a quarter warp (eight consecutive slots of a tile) read parked
+// blocks from different 16-byte bank groups at every list position: the bank group of a parked piece is the incidence's
+// tile-relative index mod 8 (staging is incidence-minor), so a greedy assignment per (group of 8 slots, position) is enough.
+// Pure reordering of commutative sums' operand lists -- deterministic, no effect on which blocks are summed.
+__global__ void k_order_lists(int64_t n_tiles, int cap, int nt, const TileHdr* __restrict__ hdr, const int2* __restrict__ ent_rel,
+                              const uint8_t* __restrict__ tile_bytes, uint32_t* __restrict__ p_src) {
+  const int64_t t = blockIdx.x;
+  if (t >= n_tiles) return;
+  const TileHdr h = hdr[t];
+  if (h.nent <= 0) return;
+  const uint8_t* s_ss = tile_bytes + h.boff;
+  const uint8_t* eos = s_ss + pad16(h.nslots + h.nent + 1);
+  uint8_t* srcb = reinterpret_cast<uint8_t*>(p_src + t * cap);
+  for (int g = threadIdx.x; g * 8 < h.nslots; g += blockDim.x) {
+    uint8_t* lst[8]; int len[8], base[8];
+    int maxlen = 0;
+    for (int l = 0; l < 8; ++l) {
+      const int ls = g * 8 + l;
+      len[l] = 0; lst[l] = nullptr; base[l] = 0;
+      if (ls >= h.nslots) continue;
+      const int le = eos[ls];
+      const int2 rel = ent_rel[h.e0 + le];
+      const uint8_t* ss = s_ss + ls + le;
+      lst[l] = srcb + 4 * rel.x + ss[0];
+      len[l] = (int)ss[1] - (int)ss[0];
+      base[l] = rel.x;
+      maxlen = max(maxlen, len[l]);
+    }
+    for (int pos = 0; pos < maxlen; ++pos) {
+      unsigned used = 0;
+      for (int l = 0; l < 8; ++l) {
+        if (pos >= len[l]) continue;
+        int pick = pos;
+        for (int c = pos; c < len[l]; ++c)
+          if (!(used >> ((base[l] + (lst[l][c] >> 2)) & 7) & 1u)) { pick = c; break; }
+        const uint8_t tmp = lst[l][pos]; lst[l][pos] = lst[l][pick]; lst[l][pick] = tmp;
+        used |= 1u << ((base[l] + (lst[l][pos] >> 2)) & 7);
+      }
+    }
+  }
+  (void)nt;
+}
+
 // per tile (CAP = 128 incidences): the DISTINCT mesh vertices its incidences touch (~40 instead of 4 x 128), and each incidence's
 // four vertices as byte positions in that list.  The pipelined kernel stages coordinates and state once per distinct vertex.
 __global__ void __launch_bounds__(128) k_tile_vlist(TileHdr* __restrict__ hdr, const int4* __restrict__ p_vtx, const int4* __restrict__ p_lead,
@@ -1171,6 +1214,10 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   k_tile_pack<<<(unsigned)n_tiles, 128, 0, s>>>(CAPV, d_tile_ent, d_inc_ptr, d_slot_ptr, d_boff, c_cell, c_vtx, c_lead,
                                                 reinterpret_cast<const uint32_t*>(c_src), d_slot_start, d_diag, P->d_tile_hdr, P->d_ent_rel,
                                                 P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes);
+  if (!getenv("NSGPU_NO_LIST_ORDER")) {
+    k_order_lists<<<(unsigned)n_tiles, 64, 0, s>>>(n_tiles, CAPV, CAPV, P->d_tile_hdr, P->d_ent_rel, P->d_tile_bytes, P->d_src);
+    ctx->launches += 1;
+  }
   if (CAPV == 128) {
     PL_CUDA(cudaMalloc(&P->d_tile_vlist, sizeof(int2) * (size_t)n_tiles * PIPE_VCAP));
     PL_CUDA(cudaMemsetAsync(P->d_tile_vlist, 0, sizeof(int2) * (size_t)n_tiles * PIPE_VCAP, s));
