@@ -251,15 +251,62 @@ __global__ void k_order_lists(int64_t n_tiles, int cap, int nt, const TileHdr* _
       base[l] = rel.x;
       maxlen = max(maxlen, len[l]);
     }
+    // per list position: maximum bipartite matching lanes -> bank groups (Kuhn's augmenting paths on an 8 x 8 problem);
+    // a lane left unmatched takes whatever it has next
     for (int pos = 0; pos < maxlen; ++pos) {
-      unsigned used = 0;
+      unsigned cand[8];          // bank groups lane l can still offer at this position
+      int owner[8];              // bank group -> lane
+      for (int b = 0; b < 8; ++b) owner[b] = -1;
+      for (int l = 0; l < 8; ++l) {
+        cand[l] = 0;
+        for (int c = pos; c < len[l]; ++c) cand[l] |= 1u << ((base[l] + (lst[l][c] >> 2)) & 7);
+      }
+      for (int l = 0; l < 8; ++l) {
+        if (!cand[l]) continue;
+        // iterative augmenting path search from lane l
+        int stack_lane[9], stack_bank[9], depth = 0;
+        unsigned visited = 0;
+        int prev_bank_of_lane[8];
+        for (int k = 0; k < 8; ++k) prev_bank_of_lane[k] = -1;
+        stack_lane[0] = l; stack_bank[0] = -1;
+        bool found = false;
+        int end_bank = -1;
+        // breadth-first over alternating paths (8 nodes: a tiny queue)
+        int queue[8], qh = 0, qt = 0, parent_lane_of_bank[8];
+        for (int b = 0; b < 8; ++b) parent_lane_of_bank[b] = -1;
+        queue[qt++] = l;
+        while (qh < qt && !found) {
+          const int cur = queue[qh++];
+          for (int b = 0; b < 8 && !found; ++b) {
+            if (!((cand[cur] >> b) & 1u) || ((visited >> b) & 1u)) continue;
+            visited |= 1u << b;
+            parent_lane_of_bank[b] = cur;
+            if (owner[b] < 0) { found = true; end_bank = b; }
+            else if (qt < 8) queue[qt++] = owner[b];
+          }
+        }
+        if (found) {   // flip the path
+          int b = end_bank;
+          while (b >= 0) {
+            const int ln = parent_lane_of_bank[b];
+            int nb = -1;
+            for (int k = 0; k < 8; ++k) if (owner[k] == ln) nb = k;   // the bank ln held before (if any)
+            owner[b] = ln;
+            if (ln == l) break;
+            b = nb;
+          }
+        }
+        (void)stack_lane; (void)stack_bank; (void)depth; (void)prev_bank_of_lane;
+      }
       for (int l = 0; l < 8; ++l) {
         if (pos >= len[l]) continue;
+        int want = -1;
+        for (int b = 0; b < 8; ++b) if (owner[b] == l) want = b;
         int pick = pos;
-        for (int c = pos; c < len[l]; ++c)
-          if (!(used >> ((base[l] + (lst[l][c] >> 2)) & 7) & 1u)) { pick = c; break; }
+        if (want >= 0)
+          for (int c = pos; c < len[l]; ++c)
+            if (((base[l] + (lst[l][c] >> 2)) & 7) == want) { pick = c; break; }
         const uint8_t tmp = lst[l][pos]; lst[l][pos] = lst[l][pick]; lst[l][pick] = tmp;
-        used |= 1u << ((base[l] + (lst[l][pos] >> 2)) & 7);
       }
     }
   }
