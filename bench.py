@@ -30,11 +30,11 @@ WORKLOADS = {  # n_cross, n_long  
 }
 NU, CI = 0.1, 36.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the assembly kernel, one launch, from the committed ncu --set full capture
-# (default kernel options, 1 GPU): 6.00 GB read + 16.46 GB written, against 21.0 GB algorithmic (the pipelined kernel reads
+# (default kernel options, 1 GPU): 6.03 GB read + 16.46 GB written, against 21.0 GB algorithmic (the pipelined kernel reads
 # one vertex list per tile instead of eight indices per incidence, which removed ~9 GB of index traffic).
-NCU_TRAFFIC = {"L": (22.46e9, "profiles/r1b_ncu_full_L_p1tet_pipe.txt")}
+NCU_TRAFFIC = {"L": (22.49e9, "profiles/r1c_ncu_full_L_p1tet_pipe.txt")}
 # executed fp64 work of the assembly kernel from the same capture: 2*DFMA + DADD + DMUL thread instructions per cell
-FLOP_PER_CELL = 5806
+FLOP_PER_CELL = 5426
 
 
 def peaks():
@@ -291,10 +291,10 @@ def run_ours(args):
                          "traffic_source": (NCU_TRAFFIC[args.workload][1] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
                          "peak_source": how, "kernel_ms": kernel_ms_avg, "algorithmic_bytes": b_jf,
                          "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): ncu shows DRAM ~9 %, "
-                                 "fp64 pipe ~37 % busy, DRAM traffic 1.07x the algorithmic bytes"},
+                                 "fp64 pipe ~38 % busy, DRAM traffic 1.07x the algorithmic bytes"},
             "fp64": {"flop_per_cell_executed": FLOP_PER_CELL, "achieved_TFLOP/s": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
                      "peak_TFLOP/s": 33.9 * world, "frac": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (33.9 * world),
-                     "source": "executed DFMA/DMUL/DADD thread instructions from ncu (profiles/r1b_ncu_full_L_p1tet_pipe.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
+                     "source": "executed DFMA/DMUL/DADD thread instructions from ncu (profiles/r1c_ncu_full_L_p1tet_pipe.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
             "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
                               "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
             "spmv": {"ms": s_ms, "GB/s": b_spmv / (s_ms * 1e-3) / 1e9, "frac": b_spmv / (s_ms * 1e-3) / 1e9 / hbm_total,
