@@ -234,7 +234,9 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
   g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
 #pragma unroll
   for (int j = 0; j < 3; ++j) g[0][j] = -(g[1][j] + g[2][j] + g[3][j]);
-  const double W = fabs(det) * (1.0 / 24.0);
+  // the caller may pin a synchronisation point here (after the geometry, before anything is parked): it gets the weight and
+  // hands it back, which ties every later quadrature sum to that point
+  const double W = scratch.after_geometry(fabs(det) * (1.0 / 24.0));
   const double V = 4.0 * W;
 
   double G[6], gk[3];   // G: xx xy xz yy yz zz (sum over the three non-origin vertices)

@@ -358,7 +358,10 @@ __global__ void __launch_bounds__(128) k_tile_vlist(TileHdr* __restrict__ hdr, c
       packed |= (uint32_t)(lo & 255) << (8 * a);
     }
   }
-  inc_loc[t * 128 + tid] = packed;
+  __shared__ uint32_t first_packed;
+  if (tid == 0) first_packed = packed;
+  __syncthreads();
+  inc_loc[t * 128 + tid] = tid < ninc ? packed : first_packed;   // padded lanes: a harmless copy of the tile's first incidence
   if (tid == 0) { hdr[t].nv = total; atomicMax(max_nv, total); }
 }
 
@@ -563,9 +566,14 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
   const FormParams &form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,  \
       const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value, const int dbg
 
-template <int CAP, bool WANT_J, bool WANT_F, class View>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `before_first_write` is called exactly once, by every thread that runs the function, before anything is written into the
+// tile view (staging area): the pipelined kernel places there the barrier that waits for the previous tile's gather, so
+// that the geometry / first quadrature point of the next tile overlap the tail of that gather.
+template <int CAP, bool WANT_J, bool WANT_F, class View, class Hook = NoHook>
 __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const int (&lead)[4], const uint32_t cm, const double (&x)[4][3],
-                                             const double (&u)[4][3], const double (&p)[4], P1_PHASE_ARGS) {
+                                             const double (&u)[4][3], const double (&p)[4], P1_PHASE_ARGS, Hook before_first_write = Hook()) {
   {
     const bool has_bc = (cm & INC_BC_BIT) != 0;
     double fr[4] = {0.0, 0.0, 0.0, 0.0};
@@ -612,7 +620,10 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
       struct SmemScratch {
         double2* st;   // staging area; the five pieces of point q wait in pieces 0..4 of the thread's (not yet written) block q
         int tid;
+        Hook& hook;
+        __device__ double after_geometry(double w) const { return w; }
         __device__ void put(int q, const P1TetPoint& pt) const {
+          if (q == 1) hook();   // first write into the view
           st[stage_idx(CAP, q, 0, tid)] = make_double2(pt.uq[0], pt.uq[1]); st[stage_idx(CAP, q, 1, tid)] = make_double2(pt.uq[2], pt.Gu[0]);
           st[stage_idx(CAP, q, 2, tid)] = make_double2(pt.Gu[1], pt.Gu[2]); st[stage_idx(CAP, q, 3, tid)] = make_double2(pt.ew, pt.eb);
           st[stage_idx(CAP, q, 4, tid)] = make_double2(pt.ea, 0.0);
@@ -623,8 +634,9 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
           pt.uq[0] = a.x; pt.uq[1] = a.y; pt.uq[2] = b.x; pt.Gu[0] = b.y;
           pt.Gu[1] = c.x; pt.Gu[2] = c.y; pt.ew = d.x; pt.eb = d.y; pt.ea = e.x;
         }
-      } scratch{v.stageJ, tid};
+      } scratch{v.stageJ, tid, before_first_write};
       if (dbg & 2) {   // timing experiment: no algebra
+        before_first_write();
         double z[16] = {x[0][0] + u[1][1] + p[2] + x[3][2] + u[3][0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int n = 0; n < 4; ++n) emit(n, z);
@@ -635,9 +647,11 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
       // residual-only pass: the Jacobian rows are needed only for the lifting term of cells that touch a Dirichlet dof
       struct LocalScratch {
         P1TetPoint q[4];
+        __device__ double after_geometry(double w) const { return w; }
         __device__ void put(int i, const P1TetPoint& pt) { q[i] = pt; }
         __device__ void get(int i, P1TetPoint& pt) const { pt = q[i]; }
       } scratch;
+      before_first_write();   // ahead of the (lane-divergent) choice below: the barrier it may hold must be reached uniformly
       if (has_bc) p1tet_rowslab2<true, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
       else p1tet_rowslab2<false, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
     }
@@ -774,7 +788,7 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
     const int s = j % 3;
     const TileHdr h = r_hdr[s];
     const uint32_t loc = r_loc(s)[tid];
-    const uint32_t cm = r_cm(s)[tid];
+    const uint32_t cm = tid < h.ninc ? r_cm(s)[tid] : 0u;   // padded lanes: plain interior copy (never the Dirichlet path)
     double x[4][3], u[4][3], p[4];
     int lead[4] = {0, 0, 0, 0};
     {
@@ -789,17 +803,26 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
         if (cm & INC_BC_BIT) lead[a] = r_vl(s)[i].y;   // first dofs are only needed by the Dirichlet path
       }
     }
-    if (h.nent > 0) tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
-    cp_async_commit();                     // group A: tables(j)
     if (j + 1 < nj) fetch_inputs(j + 1);
     if (j + 2 < nj) fetch_idx(j + 2);
-    cp_async_commit();                     // group B: vertex table(j+1), index ring(j+2), header(j+2)
-    if (tid < h.ninc) phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
-    cp_async_wait_group<1>();              // tables(j)
-    __syncthreads();
+    cp_async_commit();                     // vertex table(j+1), index ring(j+2), header(j+2)
+    // Everything above only reads what the barrier after tile j-1's algebra published, and the start of the algebra works in
+    // registers: the barrier that waits for the previous tile's gather (it frees the staging area and the gather tables)
+    // sits right before this tile's first staging write, so warps that finish their share of a gather early go on.
+    auto free_view = [&]() {
+      __syncthreads();
+      if (h.nent > 0) tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
+      cp_async_commit();                   // gather lists / row positions of this tile (needed after the algebra)
+    };
+    // padded lanes of a warp that holds real incidences run on a copy of the tile's first incidence (k_tile_vlist); a warp
+    // without any only takes part in the barrier
+    if ((tid & ~31) < h.ninc)
+      phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg, free_view);
+    else
+      free_view();
+    cp_async_wait_all();                   // this tile's tables; the prefetches have had the whole algebra to land
+    __syncthreads();                       // parked slabs and tables are complete; table(j+1), ring(j+2), header(j+2) are visible
     if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
-    cp_async_wait_all();                   // group B has had the whole tile to land
-    __syncthreads();                       // staging / tables are free again; table(j+1), ring(j+2), header(j+2) are visible
   }
 }
 

@@ -68,7 +68,7 @@ extern "C" int harness_p1tet2(double nu, double Ci, const double* x, const doubl
       for (int i = 0; i < 3; ++i) { xx[a][i] = x[3 * perm[a] + i]; uu[a][i] = w[3 * perm[a] + i]; }
       pp[a] = w[12 + perm[a]];
     }
-    struct Scratch { P1TetPoint q[4]; void put(int i, const P1TetPoint& p) { q[i] = p; } void get(int i, P1TetPoint& p) const { p = q[i]; } } sc;
+    struct Scratch { P1TetPoint q[4]; double after_geometry(double w) const { return w; } void put(int i, const P1TetPoint& p) { q[i] = p; } void get(int i, P1TetPoint& p) const { p = q[i]; } } sc;
     double blks[4][16];
     auto emit = [&](int n, const double (&b)[16]) { for (int k = 0; k < 16; ++k) blks[n][k] = b[k]; };
     p1tet_rowslab2<true, true>(f, m == 0, xx, uu, pp, fr, sc, emit);
