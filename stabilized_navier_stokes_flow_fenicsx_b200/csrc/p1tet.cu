@@ -40,7 +40,7 @@ struct TileHdr {
 
 struct nsgpu_p1tet_plan {
   int64_t n_inc = 0, n_ent = 0, n_tiles = 0, n_slots = 0;
-  int cap = 0, maxdeg = 0, max_nent = 0;   // max_nent: most vertices in one tile
+  int cap = 0, lanes = 0, maxdeg = 0, max_nent = 0;   // max_nent: most vertices in one tile
   // per incidence, TILE-PADDED: entry k of tile t lives at t * cap + k (so phase-A loads do not wait for the header)
   uint32_t* d_inc_cell = nullptr;   // cell * 4 + local vertex; bit 31: the cell touches a Dirichlet dof (refreshed when the BCs change)
   int4* d_inc_vtx = nullptr;        // geometry vertex ids, row vertex first (rotated order)
@@ -1084,7 +1084,7 @@ bool p1tet_fast_available(nsgpu_ctx* ctx) {
   if (ctx->lanes == 1 && ctx->threads > 256) ctx->threads = 256;
   if (ctx->gdim != 3 || ctx->vdeg != 1 || !ctx->pattern_built || !ctx->rows_presorted || !ctx->d_pairs) return false;
   if (ctx->n_cells_owned >= ((int64_t)1 << 29)) return false;
-  if (ctx->p1plan && ctx->p1plan->cap != plan_cap(ctx)) p1tet_free(ctx);
+  if (ctx->p1plan && (ctx->p1plan->cap != plan_cap(ctx) || ctx->p1plan->lanes != ctx->lanes)) p1tet_free(ctx);   // kernel attributes are set per plan
   if (!ctx->p1plan) {
     if (p1tet_build_plan(ctx) != NSGPU_OK) return false;
   }
@@ -1120,6 +1120,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   const int CAPV = plan_cap(ctx);
   P->n_inc = n_inc;
   P->cap = CAPV;
+  P->lanes = ctx->lanes;
   uint64_t *d_keys = nullptr, *d_keys2 = nullptr, *d_items = nullptr, *d_items2 = nullptr;
   uint32_t *d_leader = nullptr, *c_cell = nullptr;
   int4 *c_vtx = nullptr, *c_lead = nullptr;
