@@ -204,6 +204,11 @@ static void launch_generic(nsgpu_ctx* ctx, const double* d_xin, bool want_J, boo
   ctx->launches += 1;
 }
 
+__global__ void k_zero_positions(int64_t n, const int64_t* __restrict__ pos, double* vals) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) vals[pos[i]] = 0.0;
+}
+
 // assemble_matrix's BC diagonal pass on the owned rows (also used by the streamed host path)
 int k_bc_diagonal_launch(nsgpu_ctx* ctx) {
   k_bc_diagonal<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, ctx->stream>>>(ctx->n_owned, ctx->d_bc_mult, ctx->d_diag, ctx->d_vals);
@@ -224,8 +229,18 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   }
   // J.zeroEntries(): the row-owner kernel writes every entry of every locally assembled row exactly once, so the
   // zero-fill pass is only needed when rows also hold entries that only other ranks contribute to.
+  // With several ranks the entries that receive contributions of other ranks' ghost rows (the J.assemble() exchange adds
+  // into them, and some of them are entries no local cell touches) are the only ones that have to start from zero: they are
+  // exactly the receive positions of the ghost-row plan, a few 10 MB instead of the whole value array.
   const bool zero_vals = want_J && !(fast && ctx->extra_rows.empty());
-  if (zero_vals) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));
+  const bool zero_recv_only = zero_vals && fast && ctx->rows.n_neigh > 0 && !ctx->rows.recv_ptr.empty() && ctx->rows.recv_ptr.back() > 0;
+  if (zero_recv_only) {
+    const int64_t nr = ctx->rows.recv_ptr.back();
+    k_zero_positions<<<(unsigned)ceil_div(nr, 256), 256, 0, s>>>(nr, ctx->rows.d_recv_pos, ctx->d_vals);
+    ctx->launches += 1;
+  } else if (zero_vals) {
+    NS_CUDA(ctx, cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (ctx->nnz > 0 ? ctx->nnz : 1), s));
+  }
   if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_cols, s));                          // f_local.set(0.0)
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
 

@@ -43,6 +43,7 @@ def main():
         # ghosts deliberately wrong on input: the forward halo must refresh them
         xin = part.w.copy()
         xin[n_owned:] = 1e30
+        asm.set_values(np.full(asm.nnz, 1e30))        # poison: every entry must be written or explicitly zeroed by the assembly
         vals, F = asm.jacobian_residual(xin)
         ip = np.empty(n_dofs + 1, dtype=np.int64); ix = np.empty(asm.nnz, dtype=np.int32)
         asm._check(asm.lib.nsgpu_get_pattern(asm.ctx, ip.ctypes.data, ix.ctypes.data), "get_pattern")
