@@ -227,6 +227,11 @@ def run_ours(args):
         asm.jacobian_residual_dev(x_dev, False, F_dev)
         f_ms.append(asm.last_kernel_ms())
     f_ms = comm.max(float(np.mean(f_ms[3:])))
+    j_ms = []
+    for _ in range(3 + min(args.steps, 10)):
+        asm.jacobian_residual_dev(x_dev, True, None)            # Jacobian only (SURVEY 8d asks for J-only, F-only, fused, SpMV)
+        j_ms.append(asm.last_kernel_ms())
+    j_ms = comm.max(float(np.mean(j_ms[3:])))
     s_ms = []
     for _ in range(3 + min(args.steps, 10)):
         asm.spmv_dev(x_dev, y_dev)
@@ -297,6 +302,7 @@ def run_ours(args):
                      "source": "executed DFMA/DMUL/DADD thread instructions from ncu (profiles/r1c_ncu_full_L_p1tet_pipe.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
             "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
                               "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
+            "jacobian_only": {"ms": j_ms, "Mcells/s": nc_total / (j_ms * 1e-3) / 1e6},
             "spmv": {"ms": s_ms, "GB/s": b_spmv / (s_ms * 1e-3) / 1e9, "frac": b_spmv / (s_ms * 1e-3) / 1e9 / hbm_total,
                      "GFLOP/s": 2 * nnz_total / (s_ms * 1e-3) / 1e9,
                      "note": "GB/s uses the CSR byte model of BASELINE.md (12 B/nnz + vectors); the vertex-blocked kernel reads one column "
