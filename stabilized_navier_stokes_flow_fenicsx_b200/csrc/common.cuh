@@ -96,6 +96,7 @@ struct nsgpu_ctx {
   bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
   double* d_x_last = nullptr;
   int64_t fused_hits = 0;
+  int stream_chunks = 16;  // tile chunks of the streamed host path
   int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
   int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)
   int debug = 0;       // timing experiments only (bit 0: skip the gather phase, bit 1: skip the element algebra)

@@ -50,6 +50,7 @@ struct nsgpu_p1tet_plan {
   int max_nv = 0;                   // most distinct vertices in one tile
   // streamed host path (p1tet_assemble_streamed): tile chunks with the residual range each one finishes and the state prefix it needs
   int n_chunks = 0;                 // 0: not built yet, -1: numbering does not allow it
+  int chunks_requested = 0;         // ctx->stream_chunks the chunk plan was built for
   std::vector<int64_t> chunk_tile, chunk_flo, chunk_xhi;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev_h2d, ev_k;
@@ -1440,13 +1441,20 @@ __global__ void k_tile_ranges(int64_t n_tiles, const TileHdr* __restrict__ hdr, 
   out[t] = make_int2(h.nent > 0 ? rowdof[4 * h.e0] : -1, hi);
 }
 
-constexpr int STREAM_CHUNKS = 8;
+constexpr int STREAM_CHUNKS_MAX = 64;
 
 static int stream_plan(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
-  if (P->n_chunks != 0) return NSGPU_OK;
+  if (P->n_chunks != 0 && P->chunks_requested == ctx->stream_chunks) return NSGPU_OK;
+  if (P->s_h2d) { cudaStreamDestroy(P->s_h2d); P->s_h2d = nullptr; }
+  if (P->s_d2h) { cudaStreamDestroy(P->s_d2h); P->s_d2h = nullptr; }
+  for (cudaEvent_t e : P->ev_h2d) cudaEventDestroy(e);
+  for (cudaEvent_t e : P->ev_k) cudaEventDestroy(e);
+  P->ev_h2d.clear(); P->ev_k.clear();
+  P->chunks_requested = ctx->stream_chunks;
   P->n_chunks = -1;
-  if (!pipe_applies(ctx) || ctx->nranks != 1 || P->n_tiles < 4 * STREAM_CHUNKS) return NSGPU_OK;
+  const int K = ctx->stream_chunks < 1 ? 1 : (ctx->stream_chunks > STREAM_CHUNKS_MAX ? STREAM_CHUNKS_MAX : ctx->stream_chunks);
+  if (!pipe_applies(ctx) || ctx->nranks != 1 || P->n_tiles < 4 * K) return NSGPU_OK;
   int2* d_rng = nullptr;
   NS_CUDA(ctx, cudaMalloc(&d_rng, sizeof(int2) * (size_t)P->n_tiles));
   k_tile_ranges<<<g256(P->n_tiles), 256, 0, ctx->stream>>>(P->n_tiles, P->d_tile_hdr, P->d_tile_vlist, P->d_rowdof, d_rng);
@@ -1463,7 +1471,6 @@ static int stream_plan(nsgpu_ctx* ctx) {
     if (rng[t].x <= prev) return NSGPU_OK;
     prev = rng[t].x;
   }
-  const int K = STREAM_CHUNKS;
   P->chunk_tile.assign(K + 1, 0); P->chunk_flo.assign(K + 1, 0); P->chunk_xhi.assign(K, 0);
   for (int c = 0; c <= K; ++c) P->chunk_tile[c] = P->n_tiles * c / K;
   int64_t xhi = 0;
