@@ -721,13 +721,15 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
 // attributed ~22 % of the warp time to waiting for them plus ~14 % to the barrier behind them
 // (profiles/r1_ncu_full_L_p1tet_v5_and_spmv.txt).  Everything arrives in shared memory through cp.async, issued one or two
 // tiles ahead:
-//   iteration j of a persistent CTA (tiles t_j = blockIdx.x + j * gridDim.x):
+//   iteration j of a persistent CTA (tiles t_j = tile0 + blockIdx.x + j * gridDim.x):
 //     LDS own vertex positions / cell word (index ring slot j % 3), then own inputs from the vertex table (buffer j & 1)
-//     cp.async tables(j)                       [group A]  gather lists / row positions of this tile (needed after the algebra)
-//     cp.async vertex table(j+1)               [group B]  cooperative: 5 copies (3 x 8 B coordinates, 2 x 16 B state) per distinct vertex
-//     cp.async index ring(j+2), header(j+2)    [group B]
-//     element algebra (registers only), park the row slab
-//     wait_group 1 (= tables), barrier, gather + stores, wait_group 0, barrier (which also publishes table(j+1) / ring(j+2))
+//     cp.async vertex table(j+1), index ring(j+2), header(j+2)   cooperative: 5 copies (3 x 8 B coordinates, 2 x 16 B state) per vertex
+//     element algebra in registers up to the first staging write; there:
+//         barrier (every warp has finished the gather of tile j-1: staging area and gather tables are free)
+//         cp.async tables(j)                  gather lists / row positions of this tile (needed after the algebra)
+//     rest of the algebra, park the row slab
+//     wait_group 0, barrier                    (slabs + tables complete; table(j+1), ring(j+2), header(j+2) published)
+//     gather + stores                          (no barrier behind it: it sits in the next iteration's algebra)
 // Requires vertex-contiguous dofs, <= PIPE_ECAP vertices and <= PIPE_VCAP distinct mesh vertices per tile.
 constexpr int PIPE_ECAP = TILE_MAX_ENT;
 constexpr int PIPE_VREC = 5;   // double2 per vertex record: (x0 x1)(x2 -)(u0 u1)(u2 p)(pad): 80-byte stride keeps 8 consecutive records on distinct banks
