@@ -48,6 +48,7 @@ struct nsgpu_p1tet_plan {
   int2* d_tile_vlist = nullptr;     // [n_tiles][PIPE_VCAP] distinct vertices of the tile: (geometry vertex, first dof)
   uint32_t* d_inc_loc = nullptr;    // [n_tiles * cap] the incidence's four vertices as positions in that list (one byte each, row vertex first)
   int max_nv = 0;                   // most distinct vertices in one tile
+  bool rows32 = false;              // every CSR row starts on a 32-byte boundary (256-bit stores of finished row pieces)
   // streamed host path (p1tet_assemble_streamed): tile chunks with the residual range each one finishes and the state prefix it needs
   int n_chunks = 0;                 // 0: not built yet, -1: numbering does not allow it
   int chunks_requested = 0;         // ctx->stream_chunks the chunk plan was built for
@@ -110,6 +111,7 @@ __global__ void k_ent_info(int64_t n_ent, const uint32_t* __restrict__ ent_leade
     const int32_t d = members[(int64_t)A * KMAX + c];
     rowdof[e * 4 + c] = d;
     rowpos[e * 4 + c] = indptr[d];
+    if (indptr[d] & 3) not_contig[3] = 1;   // = flag [4]: row start not 32-byte aligned
     ok = ok && d == (int32_t)A + c;
   }
   if (!ok) *not_contig = 1;
@@ -455,9 +457,19 @@ __device__ __forceinline__ double quad_sum_b(double v) {
 __device__ __forceinline__ int stage_idx(const int CAP, const int n, const int k, const int i) { return (n * 8 + k) * CAP + i; }
 
 // phase B: gather the parked row slabs into finished CSR row pieces (and residual entries)
+// one finished 32-byte row piece: a single 256-bit streaming store (sm_100: STG.E.EF.256) when the rows are 32-byte aligned
+__device__ __forceinline__ void store_piece(double* dst, const double4& a, const bool wide) {
+  if (wide) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a.x), "d"(a.y), "d"(a.z), "d"(a.w) : "memory");
+  } else {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(a.x, a.y));
+    __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(a.z, a.w));
+  }
+}
+
 template <int CAP, int NT, bool WANT_J, bool WANT_F, class View>
 __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int tid, double* __restrict__ vals,
-                                            double* __restrict__ F) {
+                                            double* __restrict__ F, const bool wide = false) {
   const uint8_t* s_ss = v.bytes;
   const uint8_t* eos = v.bytes + pad16(h.nslots + h.nent + 1);
   const uint8_t* dg = eos + pad16(h.nslots);
@@ -500,8 +512,7 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         double* dst = vals + v.rowpos[4 * le + r] + 4 * s;
-        __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[r].x, acc[r].y));
-        __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc[r].z, acc[r].w));
+        store_piece(dst, acc[r], wide);
       }
     }
   }
@@ -541,8 +552,7 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
       if (le < h.nent && part == 0) {
         if (WANT_J) {
           double* dst = vals + v.rowpos[4 * le + r] + 4 * dg[le];
-          __stcs(reinterpret_cast<double2*>(dst), make_double2(acc.x, acc.y));
-          __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(acc.z, acc.w));
+          store_piece(dst, acc, wide);
         }
         if (WANT_F) {
           const int4 rd = v.rowdof[le];
@@ -825,7 +835,7 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
       free_view();
     cp_async_wait_all();                   // this tile's tables; the prefetches have had the whole algebra to land
     __syncthreads();                       // parked slabs and tables are complete; table(j+1), ring(j+2), header(j+2) are visible
-    if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+    if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F, (dbg & (1 << 30)) != 0);
   }
 }
 
@@ -1132,7 +1142,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   int64_t *d_tile_ent = nullptr, *d_tsize = nullptr, *d_boff = nullptr;
   int* d_slot_cnt = nullptr;
   void* d_tmp = nullptr;
-  int* d_flag = nullptr;   // [0] bad, [1] not contiguous, [2] most vertices in one tile, [3] most distinct mesh vertices touched by one tile
+  int* d_flag = nullptr;   // [0] bad, [1] not contiguous, [2] most vertices in one tile, [3] most distinct mesh vertices touched by one tile, [4] a row does not start on a 32-byte boundary
   auto cleanup = [&]() {
     cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_items); cudaFree(d_items2); cudaFree(d_leader); cudaFree(c_cell); cudaFree(c_vtx);
     cudaFree(c_lead); cudaFree(c_src); cudaFree(d_slot_start); cudaFree(d_diag); cudaFree(d_cnt); cudaFree(d_nrun); cudaFree(d_nslots);
@@ -1208,8 +1218,8 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   PL_SCAN(d_cnt, d_inc_ptr, n_ent + 1);
 
   // per-vertex output info and neighbour-slot prefix
-  PL_CUDA(cudaMalloc(&d_flag, 4 * sizeof(int)));
-  PL_CUDA(cudaMemsetAsync(d_flag, 0, 4 * sizeof(int), s));
+  PL_CUDA(cudaMalloc(&d_flag, 5 * sizeof(int)));
+  PL_CUDA(cudaMemsetAsync(d_flag, 0, 5 * sizeof(int), s));
   PL_CUDA(cudaMalloc(&d_nslots, sizeof(int64_t) * (n_ent + 1)));
   PL_CUDA(cudaMalloc(&d_slot_ptr, sizeof(int64_t) * (n_ent + 1)));
   PL_CUDA(cudaMalloc(&d_diag, n_ent + 1));
@@ -1298,8 +1308,8 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
     PL_CUDA(cudaMalloc(&P->d_inc_loc, sizeof(uint32_t) * (size_t)n_tiles * CAPV));
     k_tile_vlist<<<(unsigned)n_tiles, 128, 0, s>>>(P->d_tile_hdr, P->d_inc_vtx, P->d_inc_lead, P->d_tile_vlist, P->d_inc_loc, d_flag + 3);
   }
-  int flags[4] = {0, 0, 0, 0};
-  PL_CUDA(cudaMemcpyAsync(flags, d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  int flags[5] = {0, 0, 0, 0, 0};
+  PL_CUDA(cudaMemcpyAsync(flags, d_flag, 5 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PL_CUDA(cudaStreamSynchronize(s));
   PL_CUDA(cudaGetLastError());
   ctx->launches += 18;
@@ -1311,6 +1321,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->contiguous = flags[1] == 0;
   P->max_nent = flags[2];
   P->max_nv = flags[3];
+  P->rows32 = flags[4] == 0;
   P->bc_dirty = true;
   ctx->p1plan = P;
   const int lanes = ctx->lanes, cap = CAPV;
@@ -1356,7 +1367,8 @@ static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool wa
   const unsigned grid = (unsigned)(resident < nt ? resident : nt);
 #define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
                      P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
-                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, nt, P->d_tile_vlist, P->d_inc_loc, t0
+                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug | ((P->rows32 && !getenv("NSGPU_NO_WIDE_STORES")) ? (1 << 30) : 0), nt,       \
+                     P->d_tile_vlist, P->d_inc_loc, t0
   if (want_J && want_F) k_p1tet_pipe<true, true><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
   else if (want_J) k_p1tet_pipe<true, false><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
   else k_p1tet_pipe<false, true><<<grid, 128, PipeSmem<false>::bytes, s>>>(P1_PIPE_ARGS);
