@@ -220,6 +220,7 @@ int k_bc_diagonal_launch(nsgpu_ctx* ctx) {
 // d_xin: n_cols state (halo already refreshed).  d_Fout: n_cols residual (zeroed here; owned part meaningful).
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   cudaStream_t s = ctx->stream;
+  if (want_J) ctx->jac_valid = false;   // the resident values are about to change; fuse_fj callers re-validate afterwards
   bool fast = false;
   if (ctx->gdim == 3 && ctx->vdeg == 1 && ctx->form.flavour == NSGPU_FORM_GMETRIC && ctx->kernel_sel != NSGPU_KERNEL_GENERIC)
     fast = p1tet_fast_available(ctx);

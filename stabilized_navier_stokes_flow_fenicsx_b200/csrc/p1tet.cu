@@ -1534,6 +1534,7 @@ int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host
     ctx->launches += 1;
   }
   const int K = P->n_chunks;
+  ctx->jac_valid = false;   // the resident values are about to change; fuse_fj callers re-validate afterwards
   ctx->last_kernel = "p1tet_pipe (streamed host vectors)";
   // the copy streams must not overtake work still queued on the compute stream (previous users of d_xvec / d_F)
   ST_CUDA(cudaEventRecord(ctx->ev[0], s));

@@ -272,6 +272,11 @@ def test_fused_F_then_J_reuses_the_jacobian(oracle):
     assert np.abs(gv2 - v_plain).max() > 0
     asm.set_option("fuse_fj", 0); ref2 = asm.jacobian(w2); asm.set_option("fuse_fj", 1)
     np.testing.assert_array_equal(gv2, ref2)
+    # a device-side assembly at another state in between must not leave a stale "same state" behind
+    asm.residual(w)
+    xd = asm.dev_alloc(8 * asm.n_cols); asm.h2d(xd, w2)
+    asm.jacobian_residual_dev(xd, True, None); asm.sync(); asm.dev_free(xd)
+    np.testing.assert_array_equal(asm.jacobian(w), v_plain)
     asm.residual(w)
     asm.set_form(flavour=0, nu=0.05)                       # form changed after F: the resident J is stale
     gv3 = asm.jacobian(w)
