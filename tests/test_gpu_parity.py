@@ -309,6 +309,33 @@ def test_streamed_host_path_is_bitwise_identical():
     asm.close()
 
 
+def test_repeated_assemblies_are_bitwise_identical():
+    """The pipelined kernel hands tiles through cp.async rings, double-buffered tables and a barrier that sits inside the next
+    tile's algebra; a race there would show up as run-to-run differences.  (compute-sanitizer is not available on this pool.)
+    25 assemblies of the same state, alternating the device and the streamed host entry points, must agree to the last bit."""
+    m = M.duct_mesh(12, 40); sp = M.mixed_space(m, 1)
+    w = M.duct_state(sp) + 0.02 * np.random.default_rng(5).standard_normal(sp.n_dofs)
+    asm = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=1)
+    asm.set_form(flavour=0, nu=1.0 / 40); asm.set_bcs(M.duct_bcs(sp))
+    asm.create_matrix(fetch=False)
+    v0, F0 = asm.jacobian_residual(w)
+    assert asm.last_kernel_name().startswith("p1tet_pipe")
+    x_dev, F_dev = asm.dev_alloc(8 * asm.n_cols), asm.dev_alloc(8 * asm.n_cols)
+    asm.h2d(x_dev, w)
+    Fh = np.zeros(asm.n_cols)
+    for it in range(25):
+        if it % 2:
+            v, F = asm.jacobian_residual(w)
+        else:
+            asm.set_values(np.full(asm.nnz, float(it)))          # stale values must be overwritten everywhere
+            asm.jacobian_residual_dev(x_dev, True, F_dev)
+            v = asm.get_values(); asm.d2h(Fh, F_dev); F = Fh[: sp.n_dofs]
+        np.testing.assert_array_equal(v, v0)
+        np.testing.assert_array_equal(F[: sp.n_dofs], F0[: sp.n_dofs])
+    asm.dev_free(x_dev); asm.dev_free(F_dev)
+    asm.close()
+
+
 def test_two_gpu_halo_and_row_exchange():
     """NCCL path (needs >= 2 GPUs on the box; skipped on the single-GPU tier): tests/multigpu_check.py under torchrun."""
     import subprocess
