@@ -96,6 +96,7 @@ struct nsgpu_ctx {
   bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
   double* d_x_last = nullptr;
   int64_t fused_hits = 0;
+  int spmv_blocks = 5;     // vertex-blocked SpMV: resident 256-thread CTAs per SM the kernel is compiled for (4, 5 or 6)
   int stream_chunks = 16;  // tile chunks of the streamed host path
   int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
   int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)

@@ -544,6 +544,9 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->ws = value != 0;
   } else if (!strcmp(name, "fuse_fj")) {
     ctx->fuse_fj = value != 0;
+  } else if (!strcmp(name, "spmv_blocks")) {
+    NS_REQUIRE(ctx, value >= 4 && value <= 6, "set_option: spmv_blocks must be 4, 5 or 6");
+    ctx->spmv_blocks = (int)value;
   } else if (!strcmp(name, "stream_chunks")) {
     NS_REQUIRE(ctx, value >= 1 && value <= 64, "set_option: stream_chunks must be 1..64");
     ctx->stream_chunks = (int)value;

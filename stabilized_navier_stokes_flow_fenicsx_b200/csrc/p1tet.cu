@@ -1015,7 +1015,8 @@ static inline unsigned g256(int64_t n);
 // column index per block, taken from the entity pair list of the pattern build, instead of 16 int32 column indices.
 // Sixteen lanes per vertex; lane s owns neighbour s: one 32-byte load of x[B], four 32-byte loads of values (one per row,
 // contiguous across lanes), 16 FMAs; the four row sums are reduced over the lanes with shuffles.
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_spmv_block4(int64_t n_ent, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
               const uint64_t* __restrict__ pairs, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
               const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
@@ -1065,8 +1066,11 @@ int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
       if (ctx->colx_leader[k] + ctx->colx_slot[k] != (int64_t)ctx->n_dofs + (int64_t)k || ctx->colx_size[k] != 4 || ctx->colx_leader[k] % 4 != 0) P->colx_ok = 0;
   }
   if (!P->colx_ok) return 0;
-  k_spmv_block4<<<g256(P->n_ent * 16), 256, 0, ctx->stream>>>(P->n_ent, ctx->n_owned, P->d_ent_pair0, P->d_ent_ns, ctx->d_pairs, P->d_rowpos,
-                                                            reinterpret_cast<const int4*>(P->d_rowdof), ctx->d_vals, d_x, d_y);
+#define SPMV_B4(MB) k_spmv_block4<MB><<<g256(P->n_ent * 16), 256, 0, ctx->stream>>>(P->n_ent, ctx->n_owned, P->d_ent_pair0, P->d_ent_ns, ctx->d_pairs, \
+      P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof), ctx->d_vals, d_x, d_y)
+  // resident CTAs per SM the kernel is compiled for (register budget 56 / 48 / 40): option "spmv_blocks"
+  if (ctx->spmv_blocks >= 6) SPMV_B4(6); else if (ctx->spmv_blocks == 5) SPMV_B4(5); else SPMV_B4(4);
+#undef SPMV_B4
   return 1;
 }
 
