@@ -171,14 +171,10 @@ def run_ours(args):
     asm.set_bcs(part.bcs)
     if args.kernel is not None:
         asm.set_option("kernel", args.kernel)
-    if args.debug:
-        asm.set_option("debug", args.debug)
     if args.ws is not None:
         asm.set_option("ws", args.ws)
-    if args.lanes is not None:
-        asm.set_option("lanes", args.lanes)
-    if args.threads is not None:
-        asm.set_option("threads", args.threads)
+    if args.pipe is not None:
+        asm.set_option("pipe", args.pipe)
     D.attach(asm, part, comm)                                       # the library's own NCCL communicator
     D.finish_pattern_exchange(asm, part, comm)                      # pattern (+ SparsityPattern.finalize exchange), halo / ghost-row plans
     setup_s = time.perf_counter() - t_setup
@@ -343,10 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NSGPU_WORKLOAD", "L"), choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=None, help="0 auto, 1 generic, 2 fast")
-    ap.add_argument("--threads", type=int, default=None, help="CTA size of the factorised kernel")
-    ap.add_argument("--lanes", type=int, default=None, help="lanes per incidence of the factorised kernel: 1 or 4")
-    ap.add_argument("--ws", type=int, default=None, help="1: warp-specialised variant of the factorised kernel")
-    ap.add_argument("--debug", type=int, default=0, help="timing experiments: 1 skip gather phase, 2 skip element algebra")
+    ap.add_argument("--ws", type=int, default=None, help="0: do not use the warp-specialised variant of the factorised kernel")
+    ap.add_argument("--pipe", type=int, default=None, help="0: do not use the software-pipelined variant either (plain tile kernel)")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

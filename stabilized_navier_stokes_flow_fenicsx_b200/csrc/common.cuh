@@ -82,6 +82,21 @@ struct nsgpu_ctx {
   struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
   void* krylov = nullptr;                      // work vectors of the device-resident TFQMR (krylov.cu)
 
+  // internal numbering (renumber.cu): caller local dof d <-> internal dof d_perm[d]; d_perm == nullptr means identity
+  int renumber = 1;         // option: 0 never, 1 when the caller's numbering is not vertex-blocked, 2 always
+  int renumber_order = 2;   // option: entity order of the internal numbering: 1 = by leader dof, 2 = Morton order of the vertices
+  double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};   // of the geometry nodes (nsgpu_set_mesh)
+  int32_t* d_perm = nullptr;
+  int32_t* d_iperm = nullptr;
+  std::vector<int32_t> h_perm;
+  bool caller_pattern_built = false;
+  int64_t* d_indptr_c = nullptr;   // CSR pattern in the caller's numbering (built on request from the internal one)
+  int32_t* d_indices_c = nullptr;
+  double* d_vals_c = nullptr;      // values in the caller's CSR order (nsgpu_values_dev under a permutation)
+  double* d_px = nullptr;          // staging vectors of the entry points (caller-ordered copies), perm_work_n entries each
+  double* d_pF = nullptr;
+  int64_t perm_work_n = 0;
+
   // work vectors (n_dofs)
   double* d_xvec = nullptr;
   double* d_F = nullptr;
@@ -90,7 +105,7 @@ struct nsgpu_ctx {
   // options
   int kernel_sel = NSGPU_KERNEL_AUTO;
   int n_sms = 148;     // SM count of the device (nsgpu_create)
-  int ws = 0;          // row-owner kernel: warp-specialised variant (compute warpgroups + helper warpgroup)
+  int ws = 1;          // row-owner kernel: warp-specialised variant (two compute warpgroups + one gather warpgroup per SM) when it applies
   int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
   int fuse_fj = 0;     // nsgpu_residual also assembles J (one pass) and nsgpu_jacobian reuses it when called with the same state
   bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
@@ -99,10 +114,6 @@ struct nsgpu_ctx {
   int spmv_blocks = 5;     // vertex-blocked SpMV: resident 256-thread CTAs per SM the kernel is compiled for (4, 5 or 6)
   int stream_chunks = 16;  // tile chunks of the streamed host path
   int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
-  int persistent = 1;  // row-owner kernel: persistent CTAs (1) or one CTA per tile (0)
-  int debug = 0;       // timing experiments only (bit 0: skip the gather phase, bit 1: skip the element algebra)
-  int lanes = 1;       // lanes per incidence in the row-owner kernel: 1 (p1tet_rowslab) or 4 (p1tet_quad)
-  int threads = 128;   // incidences per CTA of the row-owner kernel: 128 (2 CTAs/SM), 192 or 256 (1 CTA/SM)
 
   // timing / accounting
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -164,5 +175,16 @@ int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, doub
 int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y);
 int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
 void krylov_free(nsgpu_ctx* ctx);
+// renumber.cu
+int renumber_build(nsgpu_ctx* ctx);
+void renumber_free(nsgpu_ctx* ctx);
+int perm_in(nsgpu_ctx* ctx, const double* d_src_caller, double* d_dst_internal, int64_t n_perm, int64_t n_tot);
+int perm_out(nsgpu_ctx* ctx, const double* d_src_internal, double* d_dst_caller, int64_t n_perm, int64_t n_tot);
+int perm_work(nsgpu_ctx* ctx);
+int ensure_caller_pattern(nsgpu_ctx* ctx);
+int export_values(nsgpu_ctx* ctx, double* d_dst_caller);
+int import_values(nsgpu_ctx* ctx, double* d_src_caller);
+int caller_vals_buffer(nsgpu_ctx* ctx);
+int translate_positions(nsgpu_ctx* ctx, int64_t n, const int64_t* h_pos_caller, int64_t* d_pos_internal);
 
 }  // namespace nsgpu

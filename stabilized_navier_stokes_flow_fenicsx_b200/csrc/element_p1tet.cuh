@@ -383,169 +383,6 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
   }
 }
 
-#ifdef __CUDACC__
-// ------------------------------------------------------------------------------------------------------
-// Quad-lane version of the same algebra: the four lanes of an aligned lane quad share one incidence.
-// Lane j owns quadrature point j and column block n = j.  Cell constants (gradients, grad u, metric) are
-// recomputed by every lane (cheap, no communication); the point sums are combined with a 2-step butterfly.
-// This keeps the per-thread state at ~60 doubles (vs ~100 for the one-thread version), which is what lets
-// 16 warps/SM stay resident and hide the fp64 pipeline latency.
-__device__ __forceinline__ double quad_sum(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-
-// x, u, p: all four vertices (row vertex first).  j = lane & 3.  blk[4*r + d]: row r of vertex 0, column d of
-// vertex j.  fr: residual entries of vertex 0 (identical in the four lanes).
-template <bool WANT_J, bool WANT_F>
-__device__ __forceinline__ void p1tet_quad(const FormParams& fp, const bool row_is_origin, const int j, const double (&x)[4][3],
-                                           const double (&u)[4][3], const double (&p)[4], double (&blk)[16], double (&fr)[4]) {
-  double J[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) J[i][k] = x[k + 1][i] - x[0][i];
-  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
-  const double idet = 1.0 / det;
-  double g[4][3];
-  g[1][0] = c00 * idet; g[2][0] = c01 * idet; g[3][0] = c02 * idet;
-  g[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet;
-  g[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet;
-  g[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet;
-  g[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
-  g[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
-  g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) g[0][k] = -(g[1][k] + g[2][k] + g[3][k]);
-  const double W = fabs(det) * (1.0 / 24.0);
-  const double V = 4.0 * W;
-
-  double G[6], gk[3];   // G: xx xy xz yy yz zz
-#pragma unroll
-  for (int k = 0; k < 3; ++k) gk[k] = row_is_origin ? g[1][k] : g[0][k];
-  G[0] = gk[0] * gk[0] + g[2][0] * g[2][0] + g[3][0] * g[3][0];
-  G[1] = gk[0] * gk[1] + g[2][0] * g[2][1] + g[3][0] * g[3][1];
-  G[2] = gk[0] * gk[2] + g[2][0] * g[2][2] + g[3][0] * g[3][2];
-  G[3] = gk[1] * gk[1] + g[2][1] * g[2][1] + g[3][1] * g[3][1];
-  G[4] = gk[1] * gk[2] + g[2][1] * g[2][2] + g[3][1] * g[3][2];
-  G[5] = gk[2] * gk[2] + g[2][2] * g[2][2] + g[3][2] * g[3][2];
-  const double trG = G[0] + G[3] + G[5];
-  const double GG = G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]);
-  const double itrG = 1.0 / trG;
-
-  double D[3][3], P[3], U[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    U[i] = u[0][i] + u[1][i] + u[2][i] + u[3][i];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) D[i][k] = u[0][i] * g[0][k] + u[1][i] * g[1][k] + u[2][i] * g[2][k] + u[3][i] * g[3][k];
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) P[k] = p[0] * g[0][k] + p[1] * g[1][k] + p[2] * g[2][k] + p[3] * g[3][k];
-  const double divu = D[0][0] + D[1][1] + D[2][2];
-
-  // own column vertex / own quadrature point (selects instead of dynamic register indexing)
-  double uj[3], gj[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    uj[k] = (j == 0) ? u[0][k] : (j == 1) ? u[1][k] : (j == 2) ? u[2][k] : u[3][k];
-    gj[k] = (j == 0) ? g[0][k] : (j == 1) ? g[1][k] : (j == 2) ? g[2][k] : g[3][k];
-  }
-  double uq[3], Guq[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) uq[i] = P1T_A * U[i] + P1T_E * uj[i];
-  Guq[0] = G[0] * uq[0] + G[1] * uq[1] + G[2] * uq[2];
-  Guq[1] = G[1] * uq[0] + G[3] * uq[1] + G[4] * uq[2];
-  Guq[2] = G[2] * uq[0] + G[4] * uq[1] + G[5] * uq[2];
-  const double arg = fp.Ci * fp.nu * fp.nu * GG + uq[0] * Guq[0] + uq[1] * Guq[1] + uq[2] * Guq[2];
-  const double tau = NS_RSQRT(arg);
-  const double wt = W * tau;
-  double r[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) r[k] = P[k] + uq[0] * D[0][k] + uq[1] * D[1][k] + uq[2] * D[2][k];
-  const double a0 = r[0] * g[0][0] + r[1] * g[0][1] + r[2] * g[0][2];
-  const double al = wt * a0;
-  const double be = al * tau * tau;
-
-  // point sums over the quad
-  double s[3], ZG[3], TR[3], Y3[3], Y1[3][3], Q[6], sup[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    s[i] = quad_sum(wt * uq[i]);
-    ZG[i] = quad_sum(wt * Guq[i]);
-    TR[i] = quad_sum(wt * r[i]);
-    Y3[i] = quad_sum(be * Guq[i]);
-    sup[i] = quad_sum(al * uq[i]);
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const double bg = be * Guq[d];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) Y1[d][c] = quad_sum(bg * uq[c]);
-  }
-  Q[0] = quad_sum(wt * uq[0] * uq[0]); Q[1] = quad_sum(wt * uq[0] * uq[1]); Q[2] = quad_sum(wt * uq[0] * uq[2]);
-  Q[3] = quad_sum(wt * uq[1] * uq[1]); Q[4] = quad_sum(wt * uq[1] * uq[2]); Q[5] = quad_sum(wt * uq[2] * uq[2]);
-  const double tbar = quad_sum(wt);
-  const double nuLbar = quad_sum(wt * arg) * itrG;
-  // value of u at the row vertex's point (lane 0 of the quad)
-  double uq0[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) uq0[i] = P1T_A * U[i] + P1T_E * u[0][i];
-
-  double H[3], ub[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    H[d] = D[d][0] * g[0][0] + D[d][1] * g[0][1] + D[d][2] * g[0][2];
-    ub[d] = W * (P1T_A * U[d] + P1T_E * uq0[d]);
-  }
-  const double TR0 = TR[0] * g[0][0] + TR[1] * g[0][1] + TR[2] * g[0][2];
-
-  if (WANT_F) {
-    const double pbarV = W * (p[0] + p[1] + p[2] + p[3]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      fr[c] = D[c][0] * ub[0] + D[c][1] * ub[1] + D[c][2] * ub[2] + fp.nu * V * H[c] - pbarV * g[0][c] + sup[c] + nuLbar * divu * g[0][c];
-    fr[3] = W * divu + TR0;
-  }
-  if (WANT_J) {
-    const double kap = divu * itrG;
-    const double M_off = W * (4.0 * P1T_A * P1T_A + 2.0 * P1T_A * P1T_E);
-    const double Mmn = (j == 0) ? M_off + W * P1T_E * P1T_E : M_off;
-    const double L = g[0][0] * gj[0] + g[0][1] * gj[1] + g[0][2] * gj[2];
-    const double ebn = P1T_E * be, ewn = P1T_E * wt;
-    double Sn[3], Zn[3], X3[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      Sn[d] = P1T_A * s[d] + ewn * uq[d];
-      Zn[d] = (P1T_A * ZG[d] + ewn * Guq[d]) * kap;
-      X3[d] = P1T_A * Y3[d] + ebn * Guq[d];
-    }
-    const double tn = P1T_A * tbar + ewn;
-    const double X2 = P1T_A * TR0 + P1T_E * al;
-    const double dia = ub[0] * gj[0] + ub[1] * gj[1] + ub[2] * gj[2] + fp.nu * V * L + X2;
-    const double Qm[3][3] = {{Q[0], Q[1], Q[2]}, {Q[1], Q[3], Q[4]}, {Q[2], Q[4], Q[5]}};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        double v = Mmn * D[c][d];
-        v -= P1T_A * Y1[d][c] + ebn * Guq[d] * uq[c];
-        v += Sn[c] * H[d] + Qm[c][d] * L + Zn[d] * g[0][c] + nuLbar * g[0][c] * gj[d];
-        if (c == d) v += dia;
-        blk[4 * c + d] = v;
-      }
-      blk[4 * c + 3] = s[c] * L - W * g[0][c];
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) blk[12 + d] = W * gj[d] - X3[d] + tn * H[d] + s[d] * L;
-    blk[15] = tbar * L;
-  }
-}
-
 }  // namespace nsgpu
 struct nsgpu_ctx;
 namespace nsgpu {
@@ -556,6 +393,4 @@ void p1tet_free(nsgpu_ctx* ctx);
 void p1tet_mark_bc_dirty(nsgpu_ctx* ctx);
 int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y);
 int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host);
-#endif
-
 }  // namespace nsgpu

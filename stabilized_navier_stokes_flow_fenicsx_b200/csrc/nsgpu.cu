@@ -536,10 +536,6 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "kernel")) {
     NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: kernel must be 0 (auto), 1 (generic) or 2 (fast)");
     ctx->kernel_sel = (int)value;
-  } else if (!strcmp(name, "threads")) {
-    NS_REQUIRE(ctx, value == 32 || value == 64 || value == 96 || value == 128 || value == 192 || value == 256 || value == 384 || value == 512,
-               "set_option: threads must be 32, 64, 96, 128, 192, 256, 384 or 512");
-    ctx->threads = (int)value;
   } else if (!strcmp(name, "ws")) {
     ctx->ws = value != 0;
   } else if (!strcmp(name, "fuse_fj")) {
@@ -554,13 +550,14 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {
     ctx->pipe = value != 0;
-  } else if (!strcmp(name, "persistent")) {
-    ctx->persistent = value != 0;
-  } else if (!strcmp(name, "debug")) {
-    ctx->debug = (int)value;
-  } else if (!strcmp(name, "lanes")) {
-    NS_REQUIRE(ctx, value == 1 || value == 4, "set_option: lanes must be 1 or 4");
-    ctx->lanes = (int)value;
+  } else if (!strcmp(name, "renumber")) {
+    NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: renumber must be 0 (never), 1 (when the caller's numbering is not vertex-blocked) or 2 (always)");
+    NS_REQUIRE(ctx, ctx->d_dofmap == nullptr, "set_option: renumber must be set before set_space");
+    ctx->renumber = (int)value;
+  } else if (!strcmp(name, "renumber_order")) {
+    NS_REQUIRE(ctx, value == 1 || value == 2, "set_option: renumber_order must be 1 (leader dof order) or 2 (Morton order of the vertices)");
+    NS_REQUIRE(ctx, ctx->d_dofmap == nullptr, "set_option: renumber_order must be set before set_space");
+    ctx->renumber_order = (int)value;
   } else {
     set_error(ctx, std::string("set_option: unknown option ") + name);
     return NSGPU_EINVAL;

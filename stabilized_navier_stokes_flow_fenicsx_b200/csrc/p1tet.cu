@@ -40,7 +40,7 @@ struct TileHdr {
 
 struct nsgpu_p1tet_plan {
   int64_t n_inc = 0, n_ent = 0, n_tiles = 0, n_slots = 0;
-  int cap = 0, lanes = 0, maxdeg = 0, max_nent = 0;   // max_nent: most vertices in one tile
+  int cap = 0, maxdeg = 0, max_nent = 0;   // max_nent: most vertices in one tile
   // per incidence, TILE-PADDED: entry k of tile t lives at t * cap + k (so phase-A loads do not wait for the header)
   uint32_t* d_inc_cell = nullptr;   // cell * 4 + local vertex; bit 31: the cell touches a Dirichlet dof (refreshed when the BCs change)
   int4* d_inc_vtx = nullptr;        // geometry vertex ids, row vertex first (rotated order)
@@ -66,6 +66,13 @@ struct nsgpu_p1tet_plan {
   int64_t* d_ent_pair0 = nullptr;   // [n_ent] first entry of the vertex's neighbour list in ctx->d_pairs
   int32_t* d_ent_ns = nullptr;      // [n_ent] number of neighbours (4x4 blocks per row)
   bool contiguous = false;          // every vertex's dofs are (first dof) + 0,1,2,3 and first dof is even
+  // warp-specialised kernel (p1tet_ws.cuh): per-tile blobs fetched with bulk copies
+  uint8_t* d_cblob = nullptr;       // [n_tiles][WS_CBLOB] distinct-vertex list | vertex positions | cell words
+  uint8_t* d_hblob = nullptr;       // per tile: header | vertex records | slot records | gather lists
+  uint64_t* d_hword = nullptr;      // [n_tiles] (offset / 16) << 16 | (size / 16) of the tile's H blob
+  bool ws_ok = false;
+  bool ws_attr = false;             // kernel attributes set on this context's device
+  int pipe_occ = 0;                 // resident CTAs per SM of the pipelined kernel on this context's device
   bool bc_dirty = true;
   int colx_ok = -1;                 // block SpMV: column ghosts are vertex-contiguous (-1 = not checked yet)
 };
@@ -569,13 +576,13 @@ __device__ __forceinline__ void tile_gather(const View& v, const TileHdr& h, int
       const uint32_t *__restrict__ inc_cell, const int4 *__restrict__ inc_vtx,                                                  \
       const int4 *__restrict__ inc_lead, const uint32_t *__restrict__ src, const uint8_t *__restrict__ tile_bytes,               \
       const int2 *__restrict__ ent_rel, const int64_t *__restrict__ rowpos, const int4 *__restrict__ rowdof,                     \
-      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int dbg, const int64_t n_tiles
+      const TileHdr *__restrict__ tile_hdr, double *__restrict__ vals, double *__restrict__ F, const int64_t n_tiles
 
 // phase A for one incidence: gather coordinates / state, evaluate the vertex's row slab, Dirichlet handling, park the
 // four blocks (and the residual entries) in the staging area
 #define P1_PHASE_ARGS                                                                                                      \
   const FormParams &form, const double *__restrict__ xg, const double *__restrict__ wv, const int32_t *__restrict__ members,  \
-      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value, const int dbg
+      const bool contiguous, const uint8_t *__restrict__ bc_marker, const double *__restrict__ bc_value
 
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
@@ -617,7 +624,7 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
             for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;  // constrained test row
           }
       }
-      if (WANT_J && !((dbg & 8) && blk[0] != 123.456)) {
+      if (WANT_J) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
         {
@@ -646,14 +653,7 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
           pt.Gu[1] = c.x; pt.Gu[2] = c.y; pt.ew = d.x; pt.eb = d.y; pt.ea = e.x;
         }
       } scratch{v.stageJ, tid, before_first_write};
-      if (dbg & 2) {   // timing experiment: no algebra
-        before_first_write();
-        double z[16] = {x[0][0] + u[1][1] + p[2] + x[3][2] + u[3][0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int n = 0; n < 4; ++n) emit(n, z);
-      } else {
-        p1tet_rowslab2<true, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
-      }
+      p1tet_rowslab2<true, WANT_F>(form, row_is_origin, x, u, p, fr, scratch, emit);
     } else {
       // residual-only pass: the Jacobian rows are needed only for the lifting term of cells that touch a Dirichlet dof
       struct LocalScratch {
@@ -689,7 +689,7 @@ __device__ __forceinline__ void phase_a(const View& v, const int tid, const int4
       u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
     }
   }
-  phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
+  phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value);
 }
 
 // one thread per incidence; persistent CTAs (grid = resident CTAs, each walks tiles blockIdx.x, + gridDim.x, ...)
@@ -716,10 +716,10 @@ __global__ void __launch_bounds__(CAP, MINB) k_p1tet_tiles(P1_KERNEL_ARGS) {
     }
     if (h.nent <= 0) continue;
     tile_tables_async<CAP, CAP, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
-    if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
+    if (tid < h.ninc) phase_a<CAP, WANT_J, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value);
     cp_async_wait_all();
     __syncthreads();
-    if (!(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
+    tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F);
     __syncthreads();   // staging and tables are reused by the next tile
   }
 }
@@ -753,7 +753,7 @@ template <bool WANT_J> struct PipeSmem {
 
 template <bool WANT_J, bool WANT_F>
 __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int2* __restrict__ tile_vlist, const uint32_t* __restrict__ inc_loc,
-                                                       const int64_t tile0) {   // this launch covers n_tiles tiles starting at tile0
+                                                       const int64_t tile0, const bool wide) {   // this launch covers n_tiles tiles starting at tile0
   constexpr int CAP = 128;
   using View = TileView<CAP, WANT_J, PIPE_ECAP>;
   using PS = PipeSmem<WANT_J>;
@@ -830,184 +830,18 @@ __global__ void __launch_bounds__(128, 2) k_p1tet_pipe(P1_KERNEL_ARGS, const int
     // padded lanes of a warp that holds real incidences run on a copy of the tile's first incidence (k_tile_vlist); a warp
     // without any only takes part in the barrier
     if ((tid & ~31) < h.ninc)
-      phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg, free_view);
+      phase_a_core<CAP, WANT_J, WANT_F>(v, tid, lead, cm, x, u, p, form, xg, wv, members, contiguous, bc_marker, bc_value, free_view);
     else
       free_view();
     cp_async_wait_all();                   // this tile's tables; the prefetches have had the whole algebra to land
     __syncthreads();                       // parked slabs and tables are complete; table(j+1), ring(j+2), header(j+2) are visible
-    if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F, (dbg & (1 << 30)) != 0);
+    if (h.nent > 0) tile_gather<CAP, CAP, WANT_J, WANT_F>(v, h, tid, vals, F, wide);
   }
 }
 
-// ------------------------------------------------------------------------------------------ warp-specialised ring variant
-// One persistent CTA per SM, 384 threads: two compute warpgroups (phase A, 224 registers each) feed one helper warpgroup
-// (gather + stores, 56 registers) through a RING of three staging buffers.  The CTA's tiles form a sequence k = 0, 1, 2, ...
-// (tile blockIdx.x + k * gridDim.x); tile k is evaluated by compute group k % 2 into buffer k % 3 and drained by the helper
-// in order.  A compute group therefore never waits for the gather of its own previous tile (it only needs the helper to be
-// done with tile k - 3), and the helper never holds the big register budget: the three latency chains of a tile -- input
-// gathers, element algebra, reduction + stores -- overlap instead of adding up.  Hand-off: named barriers FULL[b] = 1 + b
-// (128 producers arrive, 128 helper threads sync) and EMPTY[b] = 4 + b (helper arrives, producers sync).
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-constexpr int WS_CAP = 128;    // incidences per tile (= threads of a compute group)
-constexpr int WS_ECAP = TILE_MAX_ENT;    // vertices per tile the trimmed tables hold
-constexpr int WS_NBUF = 3;
-constexpr size_t WS_VIEW = (TileSmem<WS_CAP, WS_ECAP>::bytes(true) + sizeof(TileHdr) + 15) & ~(size_t)15;   // + a copy of the tile header
-
-template <bool WANT_F>
-__global__ void __launch_bounds__(384, 1) k_p1tet_ws(P1_KERNEL_ARGS) {
-  constexpr int CAP = WS_CAP;
-  using View = TileView<CAP, true, WS_ECAP>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int wg = threadIdx.x >> 7;         // 0, 1: compute warpgroups; 2: helper
-  const int tid = threadIdx.x & 127;
-  const int64_t nk = (n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA
-  if (wg < 2) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    for (int64_t k = wg; k < nk; k += 2) {
-      const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
-      const int b = (int)(k % WS_NBUF);
-      const View v(smem_raw + b * WS_VIEW);
-      TileHdr* s_hdr = reinterpret_cast<TileHdr*>(smem_raw + b * WS_VIEW + TileSmem<CAP, WS_ECAP>::bytes(true));
-      const int4 vt = inc_vtx[tile * CAP + tid];
-      const int4 ld = inc_lead[tile * CAP + tid];
-      const uint32_t cm = inc_cell[tile * CAP + tid];
-      const TileHdr h = tile_hdr[tile];
-      if (k + 2 < nk) {   // this group's next tile: pull its streaming inputs towards the SM
-        const int64_t nt = tile + 2 * (int64_t)gridDim.x;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_vtx + nt * CAP + tid));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_lead + nt * CAP + tid));
-        if ((tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(inc_cell + nt * CAP + tid));
-        if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_hdr + nt));
-        if ((tid & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nt * CAP + tid));
-      }
-      if (k >= WS_NBUF) named_bar_sync(4 + b, 256);        // EMPTY[b]: the helper is done with tile k - 3
-      if (h.nent > 0) tile_tables_async<CAP, CAP, true>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
-      if (tid == 0) *s_hdr = h;
-      if (tid < h.ninc) phase_a<CAP, true, WANT_F>(v, tid, vt, ld, cm, form, xg, wv, members, contiguous, bc_marker, bc_value, dbg);
-      cp_async_wait_all();
-      __threadfence_block();
-      named_bar_arrive(1 + b, 256);                         // FULL[b]
-    }
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    for (int64_t k = 0; k < nk; ++k) {
-      const int b = (int)(k % WS_NBUF);
-      const View v(smem_raw + b * WS_VIEW);
-      const TileHdr* s_hdr = reinterpret_cast<const TileHdr*>(smem_raw + b * WS_VIEW + TileSmem<CAP, WS_ECAP>::bytes(true));
-      if ((dbg & 16) && k + 4 < nk) {   // experiment: pull the gather lines (coordinates, state) of a tile two rounds ahead into L2
-        const int64_t nt = (int64_t)blockIdx.x + (k + 4) * gridDim.x;
-        const int4 pv = inc_vtx[nt * CAP + tid];
-        const int4 pl = inc_lead[nt * CAP + tid];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.y));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.z));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + 3 * (int64_t)pv.w));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.y));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.z));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(wv + pl.w));
-      }
-      named_bar_sync(1 + b, 256);                           // FULL[b]
-      const TileHdr h = *s_hdr;
-      if (h.nent > 0 && !(dbg & 1)) tile_gather<CAP, CAP, true, WANT_F>(v, h, tid, vals, F);
-      if (k + WS_NBUF < nk) named_bar_arrive(4 + b, 256);   // EMPTY[b] (nobody waits after the buffer's last tile)
-    }
-  }
-}
-
-// four lanes per incidence (p1tet_quad): a tile of CAPI incidences is a CTA of 4 * CAPI threads
-template <int CAPI, int MINB, bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(4 * CAPI, MINB) k_p1tet_quad(P1_KERNEL_ARGS) {
-  constexpr int CAP = CAPI;
-  constexpr int NT = 4 * CAPI;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const TileView<CAP, WANT_J> v(smem_raw);
-  const int tid = threadIdx.x;
-  const int64_t tile = blockIdx.x;
-  const int inc = tid >> 2, j = tid & 3;
-  const int4 vt = inc_vtx[tile * CAP + inc];
-  const int4 ld = inc_lead[tile * CAP + inc];
-  const uint32_t cm = inc_cell[tile * CAP + inc];
-  const TileHdr h = tile_hdr[tile];
-  if (h.nent <= 0) return;
-  tile_tables_async<CAP, NT, WANT_J>(v, h, tid, tile, src, tile_bytes, ent_rel, rowpos, rowdof);
-  const bool has_inc = inc < h.ninc;   // padded entries point at vertex 0 / dof 0: harmless loads, results discarded
-  {
-    const int vtx[4] = {vt.x, vt.y, vt.z, vt.w};
-    const int lead[4] = {ld.x, ld.y, ld.z, ld.w};
-    double x[4][3], u[4][3], p[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double* xp = xg + 3 * (int64_t)vtx[a];
-      x[a][0] = xp[0]; x[a][1] = xp[1]; x[a][2] = xp[2];
-      if (contiguous) {
-        const double2* wp = reinterpret_cast<const double2*>(wv + lead[a]);
-        const double2 w01 = wp[0], w23 = wp[1];
-        u[a][0] = w01.x; u[a][1] = w01.y; u[a][2] = w23.x; p[a] = w23.y;
-      } else {
-        const int4 mem = reinterpret_cast<const int4*>(members)[lead[a]];
-        u[a][0] = wv[mem.x]; u[a][1] = wv[mem.y]; u[a][2] = wv[mem.z]; p[a] = wv[mem.w];
-      }
-    }
-    double blk[16], fr[4];
-    const bool row_is_origin = (cm & 3u) == 0;
-    const bool has_bc = has_inc && (cm & INC_BC_BIT) != 0;
-    // lifting needs the Jacobian rows even in a residual-only pass; BC cells are rare, so the branch is cheap
-    if (WANT_J) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
-    else if (__any_sync(0xffffffffu, has_bc)) p1tet_quad<true, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
-    else p1tet_quad<false, WANT_F>(form, row_is_origin, j, x, u, p, blk, fr);
-
-    double lift[4] = {0.0, 0.0, 0.0, 0.0};
-    if (has_bc) {
-      const int lj = (j == 0) ? lead[0] : (j == 1) ? lead[1] : (j == 2) ? lead[2] : lead[3];
-      int cd[4], rd[4];
-      if (contiguous) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) { cd[d] = lj + d; rd[d] = lead[0] + d; }
-      } else {
-        const int4 mc = reinterpret_cast<const int4*>(members)[lj];
-        const int4 mr = reinterpret_cast<const int4*>(members)[lead[0]];
-        cd[0] = mc.x; cd[1] = mc.y; cd[2] = mc.z; cd[3] = mc.w;
-        rd[0] = mr.x; rd[1] = mr.y; rd[2] = mr.z; rd[3] = mr.w;
-      }
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        if (bc_marker[cd[d]]) {
-          const double delta = bc_value[cd[d]] - wv[cd[d]];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (WANT_F) lift[r] += blk[4 * r + d] * delta;
-            blk[4 * r + d] = 0.0;
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (bc_marker[rd[r]]) {
-#pragma unroll
-          for (int d = 0; d < 4; ++d) blk[4 * r + d] = 0.0;
-        }
-    }
-    if (WANT_F) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) fr[r] += quad_sum(lift[r]);
-    }
-    if (has_inc) {
-      if (WANT_J) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-        {
-          v.stageJ[stage_idx(CAP, j, 2 * r, inc)] = make_double2(blk[4 * r], blk[4 * r + 1]);
-          v.stageJ[stage_idx(CAP, j, 2 * r + 1, inc)] = make_double2(blk[4 * r + 2], blk[4 * r + 3]);
-        }
-      }
-      if (WANT_F && j == 0) v.stageF[inc] = make_double4(fr[0], fr[1], fr[2], fr[3]);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  tile_gather<CAP, NT, WANT_J, WANT_F>(v, h, tid, vals, F);
-}
+}  // namespace nsgpu
+#include "p1tet_ws.cuh"
+namespace nsgpu {
 
 static inline unsigned g256(int64_t n);
 // ------------------------------------------------------------------------------------------ block SpMV
@@ -1079,6 +913,7 @@ void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) return;
   cudaFree(P->d_tile_vlist); cudaFree(P->d_inc_loc); cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
+  cudaFree(P->d_cblob); cudaFree(P->d_hblob); cudaFree(P->d_hword);
   cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
   if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
   if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
@@ -1092,16 +927,11 @@ void p1tet_mark_bc_dirty(nsgpu_ctx* ctx) {
   if (ctx->p1plan) ctx->p1plan->bc_dirty = true;
 }
 
-static bool use_quad(nsgpu_ctx* ctx) { return ctx->lanes == 4; }
-static int plan_cap(nsgpu_ctx* ctx) { return use_quad(ctx) ? ctx->threads / 4 : ctx->threads; }   // incidences per tile
+static int plan_cap(nsgpu_ctx*) { return 128; }   // incidence slots per tile (array stride of the tile-padded plan arrays)
 
 bool p1tet_fast_available(nsgpu_ctx* ctx) {
-  // valid (lanes, threads) pairs: 1 x {64,128,192,256}; 4 x {256,384,512}
-  if (ctx->lanes == 4 && ctx->threads < 256) ctx->threads = 256;
-  if (ctx->lanes == 1 && ctx->threads > 256) ctx->threads = 256;
   if (ctx->gdim != 3 || ctx->vdeg != 1 || !ctx->pattern_built || !ctx->rows_presorted || !ctx->d_pairs) return false;
   if (ctx->n_cells_owned >= ((int64_t)1 << 29)) return false;
-  if (ctx->p1plan && (ctx->p1plan->cap != plan_cap(ctx) || ctx->p1plan->lanes != ctx->lanes)) p1tet_free(ctx);   // kernel attributes are set per plan
   if (!ctx->p1plan) {
     if (p1tet_build_plan(ctx) != NSGPU_OK) return false;
   }
@@ -1114,20 +944,50 @@ template <typename K> static cudaError_t smem_attr(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// the (lanes, threads) -> kernel instantiation table
-#define P1_DISPATCH(OP)                                                                                       \
-  if (lanes == 4) {                                                                                           \
-    if (cap == 128) { OP((k_p1tet_quad<128, 1, true, true>), (k_p1tet_quad<128, 1, true, false>), (k_p1tet_quad<128, 1, false, true>), 128, 512); } \
-    else if (cap == 96) { OP((k_p1tet_quad<96, 1, true, true>), (k_p1tet_quad<96, 1, true, false>), (k_p1tet_quad<96, 1, false, true>), 96, 384); } \
-    else { OP((k_p1tet_quad<64, 2, true, true>), (k_p1tet_quad<64, 2, true, false>), (k_p1tet_quad<64, 2, false, true>), 64, 256); }             \
-  } else {                                                                                                    \
-    if (cap == 256) { OP((k_p1tet_tiles<256, 1, true, true>), (k_p1tet_tiles<256, 1, true, false>), (k_p1tet_tiles<256, 1, false, true>), 256, 256); } \
-    else if (cap == 192) { OP((k_p1tet_tiles<192, 1, true, true>), (k_p1tet_tiles<192, 1, true, false>), (k_p1tet_tiles<192, 1, false, true>), 192, 192); } \
-    else if (cap == 128) { OP((k_p1tet_tiles<128, 2, true, true>), (k_p1tet_tiles<128, 2, true, false>), (k_p1tet_tiles<128, 2, false, true>), 128, 128); } \
-    else if (cap == 96) { OP((k_p1tet_tiles<96, 3, true, true>), (k_p1tet_tiles<96, 3, true, false>), (k_p1tet_tiles<96, 3, false, true>), 96, 96); } \
-    else if (cap == 64) { OP((k_p1tet_tiles<64, 4, true, true>), (k_p1tet_tiles<64, 4, true, false>), (k_p1tet_tiles<64, 4, false, true>), 64, 64); }   \
-    else { OP((k_p1tet_tiles<32, 8, true, true>), (k_p1tet_tiles<32, 8, true, false>), (k_p1tet_tiles<32, 8, false, true>), 32, 32); }             \
+// per-tile blobs of the warp-specialised kernel (p1tet_ws.cuh), from the finished tile tables of the plan
+static int ws_build_tables(nsgpu_ctx* ctx) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  cudaStream_t s = ctx->stream;
+  const int64_t nt = P->n_tiles;
+  P->ws_ok = false;
+  if (nt <= 0) return NSGPU_OK;
+  int64_t *d_sz = nullptr, *d_off = nullptr;
+  int* d_flag = nullptr;
+  void* d_tmp = nullptr;
+  cudaError_t e = cudaMalloc(&d_sz, sizeof(int64_t) * (nt + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, sizeof(int64_t) * (nt + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), s);
+  int64_t total = 0;
+  int flag = 1;
+  if (e == cudaSuccess) {
+    k_ws_hsizes<<<g256(nt + 1), 256, 0, s>>>(nt, P->d_tile_hdr, P->d_ent_rel, P->d_tile_bytes, d_sz);
+    size_t tb = 0;
+    e = cub::DeviceScan::ExclusiveSum(nullptr, tb, d_sz, d_off, nt + 1, s);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tb);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_sz, d_off, nt + 1, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_off + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   }
+  if (e == cudaSuccess) e = cudaMalloc(&P->d_hblob, (size_t)total + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&P->d_hword, sizeof(uint64_t) * nt);
+  if (e == cudaSuccess) e = cudaMalloc(&P->d_cblob, (size_t)nt * WS_CBLOB);
+  if (e == cudaSuccess) {
+    k_ws_hfill<<<(unsigned)nt, 128, 0, s>>>(P->d_tile_hdr, P->d_ent_rel, P->d_tile_bytes, P->d_src, P->d_rowpos, P->d_rowdof, d_off, P->d_hblob,
+                                            P->d_hword, d_flag);
+    if (!getenv("NSGPU_NO_LIST_ORDER")) k_ws_order<<<(unsigned)nt, 32, 0, s>>>(nt, P->d_hword, P->d_hblob);
+    k_ws_cblob<<<(unsigned)nt, 128, 0, s>>>(P->d_tile_hdr, P->d_tile_vlist, P->d_inc_loc, P->d_cblob);
+    e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    ctx->launches += 4;
+  }
+  cudaFree(d_sz); cudaFree(d_off); cudaFree(d_flag); cudaFree(d_tmp);
+  if (e != cudaSuccess) { set_error(ctx, std::string("p1tet plan (warp-specialised tables): ") + cudaGetErrorString(e)); return NSGPU_ECUDA; }
+  P->ws_ok = flag == 0;
+  if (!P->ws_ok) { cudaFree(P->d_hblob); cudaFree(P->d_hword); cudaFree(P->d_cblob); P->d_hblob = nullptr; P->d_hword = nullptr; P->d_cblob = nullptr; }
+  return NSGPU_OK;
+}
 
 int p1tet_build_plan(nsgpu_ctx* ctx) {
   cudaStream_t s = ctx->stream;
@@ -1137,7 +997,6 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   const int CAPV = plan_cap(ctx);
   P->n_inc = n_inc;
   P->cap = CAPV;
-  P->lanes = ctx->lanes;
   uint64_t *d_keys = nullptr, *d_keys2 = nullptr, *d_items = nullptr, *d_items2 = nullptr;
   uint32_t *d_leader = nullptr, *c_cell = nullptr;
   int4 *c_vtx = nullptr, *c_lead = nullptr;
@@ -1270,14 +1129,18 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   // tiles: consecutive vertices packed greedily -- a tile closes when the next vertex's incidences would not fit the CAPV
   // lanes any more (or at TILE_MAX_ENT vertices, which keeps the per-vertex tables of the trimmed kernels small).  The scan
   // is inherently sequential but trivial, so it runs on the host over the incidence prefix (8 bytes per vertex, one-off).
-  std::vector<int64_t> h_inc_ptr((size_t)n_ent + 1), h_tile_ent;
+  std::vector<int64_t> h_inc_ptr((size_t)n_ent + 1), h_slot_ptr((size_t)n_ent + 1), h_tile_ent;
   PL_CUDA(cudaMemcpy(h_inc_ptr.data(), d_inc_ptr, sizeof(int64_t) * (n_ent + 1), cudaMemcpyDeviceToHost));
-  h_tile_ent.reserve((size_t)(n_inc / (CAPV > 16 ? CAPV - 16 : 1)) + 16);
+  PL_CUDA(cudaMemcpy(h_slot_ptr.data(), d_slot_ptr, sizeof(int64_t) * (n_ent + 1), cudaMemcpyDeviceToHost));
+  // caps: WS_SS incidences (staging columns of the warp-specialised kernel) and WS_VCAP neighbour slots in total, which
+  // bounds the distinct mesh vertices a tile touches (its vertex table) and its off-diagonal slots
+  const int64_t inc_cap = CAPV < WS_SS ? CAPV : WS_SS;
+  h_tile_ent.reserve((size_t)(n_inc / (inc_cap > 16 ? inc_cap - 16 : 1)) + 16);
   for (int64_t e = 0; e < n_ent;) {
     h_tile_ent.push_back(e);
-    const int64_t i0 = h_inc_ptr[e];
+    const int64_t i0 = h_inc_ptr[e], s0 = h_slot_ptr[e];
     int64_t e1 = e + 1;
-    while (e1 < n_ent && h_inc_ptr[e1 + 1] - i0 <= CAPV && e1 - e < TILE_MAX_ENT) ++e1;
+    while (e1 < n_ent && h_inc_ptr[e1 + 1] - i0 <= inc_cap && h_slot_ptr[e1 + 1] - s0 <= WS_VCAP && e1 - e < TILE_MAX_ENT) ++e1;
     e = e1;
   }
   const int64_t n_tiles = (int64_t)h_tile_ent.size();
@@ -1328,23 +1191,47 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->rows32 = flags[4] == 0;
   P->bc_dirty = true;
   ctx->p1plan = P;
-  const int lanes = ctx->lanes, cap = CAPV;
-  cudaError_t e = cudaSuccess;
-#define P1_ATTR(KJF, KJ, KF, CAPC, NTC)                                                      \
-  if (e == cudaSuccess) e = smem_attr(KJF, TileSmem<CAPC>::bytes(true));                      \
-  if (e == cudaSuccess) e = smem_attr(KJ, TileSmem<CAPC>::bytes(true));                       \
-  if (e == cudaSuccess) e = smem_attr(KF, TileSmem<CAPC>::bytes(false));
-  P1_DISPATCH(P1_ATTR)
-#undef P1_ATTR
+  if (P->contiguous && P->d_tile_vlist && P->max_nv <= WS_VCAP && P->max_nent <= TILE_MAX_ENT) {
+    int rc = ws_build_tables(ctx);
+    if (rc != NSGPU_OK) { p1tet_free(ctx); return rc; }
+  }
+  cudaError_t e = smem_attr(k_p1tet_tiles<128, 2, true, true>, TileSmem<128>::bytes(true));
+  if (e == cudaSuccess) e = smem_attr(k_p1tet_tiles<128, 2, true, false>, TileSmem<128>::bytes(true));
+  if (e == cudaSuccess) e = smem_attr(k_p1tet_tiles<128, 2, false, true>, TileSmem<128>::bytes(false));
   if (e != cudaSuccess) { set_error(ctx, std::string("p1tet plan: smem attribute: ") + cudaGetErrorString(e)); p1tet_free(ctx); return NSGPU_ECUDA; }
   return NSGPU_OK;
 #undef PL_CUDA
 #undef PL_SCAN
 }
 
+static bool ws_applies(nsgpu_ctx* ctx) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  return P && ctx->ws && P->ws_ok && P->d_cblob;
+}
+
+// warp-specialised persistent kernel, one 384-thread CTA per SM, over the tiles [t0, t1)
+static int ws_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  if (!P->ws_attr) {
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<true>::bytes));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<true>::bytes));
+    NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<false>::bytes));
+    P->ws_attr = true;
+  }
+  const int64_t nt = t1 - t0;
+  if (nt <= 0) return NSGPU_OK;
+  const unsigned grid = (unsigned)(ctx->n_sms < nt ? ctx->n_sms : nt);
+#define P1_WS_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_bc_marker, ctx->d_bc_value, P->d_cblob, P->d_hblob, P->d_hword, ctx->d_vals, d_Fout, nt, t0, P->rows32
+  if (want_J && want_F) k_p1tet_ws<true, true><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
+  else if (want_J) k_p1tet_ws<true, false><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
+  else k_p1tet_ws<false, true><<<grid, 384, WsSmem<false>::bytes, ctx->stream>>>(P1_WS_ARGS);
+#undef P1_WS_ARGS
+  return NSGPU_OK;
+}
+
 static bool pipe_applies(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
-  return P && ctx->pipe && !ctx->ws && ctx->lanes == 1 && P->cap == 128 && P->contiguous && P->max_nent <= PIPE_ECAP && P->max_nv <= PIPE_VCAP &&
+  return P && ctx->pipe && P->cap == 128 && P->contiguous && P->max_nent <= PIPE_ECAP && P->max_nv <= PIPE_VCAP &&
          P->d_tile_vlist;
 }
 
@@ -1352,7 +1239,7 @@ static bool pipe_applies(nsgpu_ctx* ctx) {
 static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   cudaStream_t s = ctx->stream;
-  static int pipe_occ = 0;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2)
+  int& pipe_occ = P->pipe_occ;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2); per context = per device
   if (!pipe_occ) {
     NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
     NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeSmem<true>::bytes));
@@ -1371,8 +1258,7 @@ static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool wa
   const unsigned grid = (unsigned)(resident < nt ? resident : nt);
 #define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
                      P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
-                     P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug | ((P->rows32 && !getenv("NSGPU_NO_WIDE_STORES")) ? (1 << 30) : 0), nt,       \
-                     P->d_tile_vlist, P->d_inc_loc, t0
+                     P->d_tile_hdr, ctx->d_vals, d_Fout, nt, P->d_tile_vlist, P->d_inc_loc, t0, P->rows32
   if (want_J && want_F) k_p1tet_pipe<true, true><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
   else if (want_J) k_p1tet_pipe<true, false><<<grid, 128, PipeSmem<true>::bytes, s>>>(P1_PIPE_ARGS);
   else k_p1tet_pipe<false, true><<<grid, 128, PipeSmem<false>::bytes, s>>>(P1_PIPE_ARGS);
@@ -1387,10 +1273,18 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   if (P->n_tiles == 0) return NSGPU_OK;
   if (P->bc_dirty) {
     k_inc_bc<<<g256(P->n_tiles * P->cap), 256, 0, s>>>(P->n_tiles * P->cap, P->d_inc_cell, ctx->d_dofmap, ctx->has_bc ? ctx->d_bc_marker : nullptr);
+    if (P->d_cblob) k_ws_cm<<<g256(P->n_tiles * 128), 256, 0, s>>>(P->n_tiles * 128, P->d_tile_hdr, P->d_inc_cell, P->d_cblob);
     P->bc_dirty = false;
-    ctx->launches += 1;
+    ctx->launches += 2;
   }
-  const int lanes = ctx->lanes, cap = P->cap;
+  if (ws_applies(ctx)) {
+    ctx->last_kernel = "p1tet_ws";
+    int rc = ws_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
+    if (rc != NSGPU_OK) return rc;
+    ctx->launches += 1;
+    NS_CUDA(ctx, cudaGetLastError());
+    return NSGPU_OK;
+  }
   if (pipe_applies(ctx)) {
     ctx->last_kernel = "p1tet_pipe";
     int rc = pipe_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
@@ -1399,42 +1293,16 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
     NS_CUDA(ctx, cudaGetLastError());
     return NSGPU_OK;
   }
-  if (ctx->ws && want_J && lanes == 1 && cap == WS_CAP && P->max_nent <= WS_ECAP) {
-    // warp-specialised persistent ring kernel: one CTA per SM
-    ctx->last_kernel = "p1tet_ws";
-    constexpr size_t SMEM = WS_NBUF * WS_VIEW;
-    const unsigned grid = (unsigned)(ctx->n_sms < P->n_tiles ? ctx->n_sms : P->n_tiles);
-    static bool attr_set = false;
-    if (!attr_set) {
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      attr_set = true;
-    }
-    if (want_F)
-      k_p1tet_ws<true><<<grid, 384, SMEM, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value,
-          P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
-          reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
-    else
-      k_p1tet_ws<false><<<grid, 384, SMEM, s>>>(ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value,
-          P->d_inc_cell, P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,
-          reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles);
-    ctx->launches += 1;
-    NS_CUDA(ctx, cudaGetLastError());
-    return NSGPU_OK;
-  }
 #define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
-                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, ctx->debug, P->n_tiles
-  // one-thread kernels are persistent (grid = resident CTAs); the quad kernels take one tile per CTA
-  ctx->last_kernel = lanes == 4 ? "p1tet_quad" : "p1tet_tiles";
-  const int64_t resident = (int64_t)ctx->n_sms * (cap == 128 ? 2 : (cap == 96 ? 3 : (cap == 64 ? 4 : (cap == 32 ? 8 : 1))));
-  const unsigned grid = (unsigned)((lanes == 4 || ctx->persistent == 0) ? P->n_tiles : (resident < P->n_tiles ? resident : P->n_tiles));
-#define P1_RUN(KJF, KJ, KF, CAPC, NTC)                                                                     \
-  if (want_J && want_F) KJF<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                        \
-  else if (want_J) KJ<<<grid, NTC, TileSmem<CAPC>::bytes(true), s>>>(P1_ARGS);                              \
-  else KF<<<grid, NTC, TileSmem<CAPC>::bytes(false), s>>>(P1_ARGS);
-  P1_DISPATCH(P1_RUN)
-#undef P1_RUN
+                reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, P->n_tiles
+  // plain tile kernel (any entity-consistent numbering): persistent, 2 CTAs per SM
+  ctx->last_kernel = "p1tet_tiles";
+  const int64_t resident = (int64_t)ctx->n_sms * 2;
+  const unsigned grid = (unsigned)(resident < P->n_tiles ? resident : P->n_tiles);
+  if (want_J && want_F) k_p1tet_tiles<128, 2, true, true><<<grid, 128, TileSmem<128>::bytes(true), s>>>(P1_ARGS);
+  else if (want_J) k_p1tet_tiles<128, 2, true, false><<<grid, 128, TileSmem<128>::bytes(true), s>>>(P1_ARGS);
+  else k_p1tet_tiles<128, 2, false, true><<<grid, 128, TileSmem<128>::bytes(false), s>>>(P1_ARGS);
 #undef P1_ARGS
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
@@ -1521,7 +1389,7 @@ __global__ void k_set_bc_range(int64_t lo, int64_t hi, const uint8_t* __restrict
 // returns 1 when the streamed path ran (J resident in ctx->d_vals, F in F_host and ctx->d_F), 0 when it does not apply
 int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host) {
   if (ctx->nranks != 1 || ctx->gdim != 3 || ctx->vdeg != 1 || ctx->form.flavour != NSGPU_FORM_GMETRIC || ctx->kernel_sel == NSGPU_KERNEL_GENERIC ||
-      !ctx->extra_rows.empty() || ctx->debug)
+      !ctx->extra_rows.empty())
     return 0;
   if (!p1tet_fast_available(ctx) || !pipe_applies(ctx)) return 0;
   nsgpu_p1tet_plan* P = ctx->p1plan;
@@ -1534,12 +1402,14 @@ int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host
   } while (0)
   if (P->bc_dirty) {
     k_inc_bc<<<g256(P->n_tiles * P->cap), 256, 0, s>>>(P->n_tiles * P->cap, P->d_inc_cell, ctx->d_dofmap, ctx->has_bc ? ctx->d_bc_marker : nullptr);
+    if (P->d_cblob) k_ws_cm<<<g256(P->n_tiles * 128), 256, 0, s>>>(P->n_tiles * 128, P->d_tile_hdr, P->d_inc_cell, P->d_cblob);
     P->bc_dirty = false;
-    ctx->launches += 1;
+    ctx->launches += 2;
   }
   const int K = P->n_chunks;
   ctx->jac_valid = false;   // the resident values are about to change; fuse_fj callers re-validate afterwards
-  ctx->last_kernel = "p1tet_pipe (streamed host vectors)";
+  const bool use_ws = ws_applies(ctx);
+  ctx->last_kernel = use_ws ? "p1tet_ws (streamed host vectors)" : "p1tet_pipe (streamed host vectors)";
   // the copy streams must not overtake work still queued on the compute stream (previous users of d_xvec / d_F)
   ST_CUDA(cudaEventRecord(ctx->ev[0], s));
   ST_CUDA(cudaStreamWaitEvent(P->s_h2d, ctx->ev[0], 0));
@@ -1555,7 +1425,8 @@ int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host
   }
   for (int c = 0; c < K; ++c) {
     ST_CUDA(cudaStreamWaitEvent(s, P->ev_h2d[c], 0));
-    int rc = pipe_launch(ctx, ctx->d_xvec, true, true, ctx->d_F, P->chunk_tile[c], P->chunk_tile[c + 1]);
+    int rc = use_ws ? ws_launch(ctx, ctx->d_xvec, true, true, ctx->d_F, P->chunk_tile[c], P->chunk_tile[c + 1])
+                    : pipe_launch(ctx, ctx->d_xvec, true, true, ctx->d_F, P->chunk_tile[c], P->chunk_tile[c + 1]);
     if (rc != NSGPU_OK) return rc;
     const int64_t lo = P->chunk_flo[c], hi = P->chunk_flo[c + 1];
     if (ctx->has_bc && hi > lo) {   // set_bc(F, bc, x, -1.0) on the rows this chunk finished

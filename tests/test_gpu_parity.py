@@ -86,23 +86,22 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     asm.close()
 
 
-@pytest.mark.parametrize("kernel,lanes,threads,ws,pipe", [(1, 1, 128, 0, 0), (2, 1, 64, 0, 0), (2, 1, 128, 0, 0), (2, 1, 128, 0, 1), (2, 1, 128, 1, 0),
-                                                           (2, 1, 192, 0, 0), (2, 1, 256, 0, 0), (2, 4, 256, 0, 0), (2, 4, 384, 0, 0), (2, 4, 512, 0, 0)])
-def test_generic_and_fast_kernels_agree(oracle, kernel, lanes, threads, ws, pipe):
-    """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernel, which must apply;
-    lanes 1: one thread per incidence, lanes 4: four lanes per incidence; ws: warp-specialised ring variant;
-    pipe: software-pipelined variant (the default)."""
+@pytest.mark.parametrize("kernel,ws,pipe,expect", [(1, 0, 0, "generic_row"), (2, 1, 1, "p1tet_ws"), (2, 0, 1, "p1tet_pipe"), (2, 0, 0, "p1tet_tiles")])
+def test_generic_and_fast_kernels_agree(oracle, kernel, ws, pipe, expect):
+    """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernels, which must apply:
+    ws = warp-specialised kernel (two compute warpgroups + a gather warpgroup per SM, the default), pipe = software-pipelined
+    2-CTA kernel, neither = plain tile kernel (the one that needs no vertex-blocked numbering)."""
     m, sp, w, bcs, fk = _case("duct_p1")
     w = w + 0.01 * np.random.default_rng(4).standard_normal(sp.n_dofs)     # off the Dirichlet values: lifting active
     indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
     asm = _gpu(m, sp, bcs, fk, kernel)
-    asm.set_option("lanes", lanes)
-    asm.set_option("threads", threads)
     asm.set_option("ws", ws)
     asm.set_option("pipe", pipe)
     asm.create_matrix(fetch=False)
     asm.set_values(np.full(asm.nnz, 1e30))                                  # poison: the row-owner kernels skip J.zeroEntries()
+    asm.set_option("stream_host", 0)
     gv, gF = asm.jacobian_residual(w)
+    assert asm.last_kernel_name() == expect
     assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
     assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
     gF2 = asm.residual(w)                                                   # residual-only pass (lifting still needs J rows)
@@ -182,7 +181,7 @@ def test_irregular_mesh_vertex_blocked_numbering(oracle):
     for stream_host in (1, 0):
         asm.set_option("stream_host", stream_host)
         gv, gF = asm.jacobian_residual(w)
-        assert asm.last_kernel_name() == ("p1tet_pipe (streamed host vectors)" if stream_host else "p1tet_pipe")
+        assert asm.last_kernel_name() == ("p1tet_ws (streamed host vectors)" if stream_host else "p1tet_ws")
         assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
         assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
     xv = rng.standard_normal(n)
@@ -319,7 +318,7 @@ def test_repeated_assemblies_are_bitwise_identical():
     asm.set_form(flavour=0, nu=1.0 / 40); asm.set_bcs(M.duct_bcs(sp))
     asm.create_matrix(fetch=False)
     v0, F0 = asm.jacobian_residual(w)
-    assert asm.last_kernel_name().startswith("p1tet_pipe")
+    assert asm.last_kernel_name().startswith("p1tet_ws")
     x_dev, F_dev = asm.dev_alloc(8 * asm.n_cols), asm.dev_alloc(8 * asm.n_cols)
     asm.h2d(x_dev, w)
     Fh = np.zeros(asm.n_cols)
