@@ -274,7 +274,7 @@ def run_ours(args):
     hbm, how = peaks()
     hbm_total = hbm * world
 
-    default_opts = args.kernel is None and args.threads is None and args.lanes is None and args.ws is None and not args.debug
+    default_opts = args.kernel is None and args.ws is None and args.pipe is None
     if rank == 0:
         value = nc_total / (ms_per_step * 1e-3) / 1e6
         achieved = b_jf / (kernel_ms_avg * 1e-3) / 1e9

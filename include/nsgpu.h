@@ -37,7 +37,8 @@ enum {
   NSGPU_ECUDA = -2,    /* CUDA runtime error (no device, OOM, launch failure) */
   NSGPU_EUNSUPPORTED = -3,
   NSGPU_ENCCL = -4,
-  NSGPU_EPATTERN = -5  /* element entry outside the sparsity pattern / row too long */
+  NSGPU_EPATTERN = -5, /* element entry outside the sparsity pattern / row too long */
+  NSGPU_ENONFINITE = -6 /* the assembled residual holds NaN / Inf (diverged state or degenerate cell); see option "check_finite" */
 };
 
 /* weak-form flavours (nsgpu_set_form) */
@@ -151,15 +152,20 @@ int nsgpu_memcpy_d2h(nsgpu_ctx* ctx, void* dst_host, const void* src_dev, int64_
 int nsgpu_host_alloc_pinned(int64_t bytes, void** out);
 int nsgpu_host_free_pinned(void* p);
 
-/* Options: "kernel" (NSGPU_KERNEL_*); for the factorised kernel "pipe" (1, default: software-pipelined variant whose
- * inputs arrive through cp.async one tile ahead), "ws" (1: warp-specialised ring variant), "lanes" (1 or 4 lanes per
- * vertex-cell incidence), "threads" (CTA size: 64..256 with 1 lane, 256..512 with 4 lanes), "persistent", and "debug"
- * (timing experiments only). */
+/* Options: "kernel" (NSGPU_KERNEL_*); for the factorised P1-P1 kernels "ws" (1, default: warp-specialised kernel -- two
+ * compute warpgroups and a gather warpgroup per SM, tables by cp.async.bulk) and "pipe" (1: software-pipelined 2-CTA kernel
+ * when "ws" is off or does not apply; both 0: plain tile kernel); "fuse_fj", "stream_host", "stream_chunks", "spmv_blocks";
+ * "check_finite" (1, default: NaN / Inf scan of every assembled residual, status NSGPU_ENONFINITE);
+ * "renumber" (0 never, 1 default: internal vertex-blocked numbering when the caller's W.dofmap.list is not vertex-blocked,
+ * 2 always) and "renumber_order" (1 leader-dof order, 2 default: Morton order of the vertices) -- both before nsgpu_set_space. */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
-/* Which assembly kernel variant the last residual / Jacobian call ran: "p1tet_pipe", "p1tet_pipe (streamed host vectors)",
- * "p1tet_tiles", "p1tet_ws", "p1tet_quad", "generic_coop", "generic_row" (static string, never NULL). */
+/* Which assembly kernel variant the last residual / Jacobian call ran: "p1tet_ws", "p1tet_ws (streamed host vectors)",
+ * "p1tet_pipe", "p1tet_pipe (streamed host vectors)", "p1tet_tiles", "generic_coop", "generic_row" (static string, never NULL). */
 const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx);
+/* Which MatMult kernel the last nsgpu_spmv* / Krylov product ran: "spmv_block4" (vertex-blocked 4x4 blocks, one column index
+ * per block) or "spmv_csr". */
+const char* nsgpu_last_spmv_name(const nsgpu_ctx* ctx);
 
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.
  * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build. */

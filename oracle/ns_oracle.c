@@ -477,6 +477,61 @@ void oracle_spmv(int64_t n_rows, const int64_t *indptr, const int32_t *indices, 
   }
 }
 
+/* CSR sparsity pattern = sorted-unique union over cells of dofs x dofs (create_matrix(problem.a),
+ * NavierStokes/NavierStokesChannelFlow.py:272), for meshes where the NumPy set-union of oracle.py is too slow.
+ * Row-by-row: the cells incident to a row dof (counting sort of the dofmap), their dofs gathered, sorted, made unique.
+ * Call once with indices == NULL (fills indptr, returns nnz), then again with the index array. */
+static int cmp_i32(const void *a, const void *b) {
+  const int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
+  return (x > y) - (x < y);
+}
+
+int64_t oracle_build_pattern(int nd, int64_t n_cells, const int32_t *dofmap, int64_t n_rows, int64_t *indptr, int32_t *indices) {
+  int64_t *start = (int64_t *)calloc((size_t)n_rows + 2, sizeof(int64_t));
+  int32_t *inc = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_cells * nd > 0 ? n_cells * nd : 1));
+  if (!start || !inc) { free(start); free(inc); return -1; }
+  for (int64_t k = 0; k < n_cells * nd; ++k) start[dofmap[k] + 2] += 1;
+  for (int64_t r = 0; r < n_rows; ++r) start[r + 2] += start[r + 1];
+  for (int64_t c = 0; c < n_cells; ++c)
+    for (int j = 0; j < nd; ++j) inc[start[dofmap[c * nd + j] + 1]++] = (int32_t)c;
+  /* now start[r] .. start[r+1] are the cells of row r */
+  int bad = 0;
+  if (!indices) indptr[0] = 0;
+#pragma omp parallel
+  {
+    int cap = 4096;
+    int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
+#pragma omp for schedule(dynamic, 4096)
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int64_t nc = start[r + 1] - start[r];
+      if (nc * nd > cap) {
+        cap = (int)(nc * nd) * 2;
+        free(buf);
+        buf = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
+      }
+      if (!buf) { bad = 1; continue; }
+      int n = 0;
+      for (int64_t k = start[r]; k < start[r + 1]; ++k)
+        for (int j = 0; j < nd; ++j) buf[n++] = dofmap[(int64_t)inc[k] * nd + j];
+      qsort(buf, (size_t)n, sizeof(int32_t), cmp_i32);
+      int m = 0;
+      for (int k = 0; k < n; ++k)
+        if (k == 0 || buf[k] != buf[k - 1]) buf[m++] = buf[k];
+      if (!indices) indptr[r + 1] = m;
+      else {
+        if (indptr[r + 1] - indptr[r] != m) { bad = 1; continue; }
+        memcpy(indices + indptr[r], buf, sizeof(int32_t) * (size_t)m);
+      }
+    }
+    free(buf);
+  }
+  free(start); free(inc);
+  if (bad) return -1;
+  if (!indices)
+    for (int64_t r = 0; r < n_rows; ++r) indptr[r + 1] += indptr[r];
+  return indptr[n_rows];
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

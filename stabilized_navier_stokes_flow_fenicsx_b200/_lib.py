@@ -59,6 +59,7 @@ SIGNATURES = {
     "nsgpu_host_alloc_pinned": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
     "nsgpu_host_free_pinned": (ctypes.c_int, [ctypes.c_void_p]),
     "nsgpu_last_kernel_name": (ctypes.c_char_p, [c_ctx]),
+    "nsgpu_last_spmv_name": (ctypes.c_char_p, [c_ctx]),
     "nsgpu_set_option": (ctypes.c_int, [c_ctx, ctypes.c_char_p, ctypes.c_int64]),
     "nsgpu_timers": (ctypes.c_int, [c_ctx, c_f64p, ctypes.c_int]),
     "nsgpu_launch_count": (ctypes.c_int64, [c_ctx]),

@@ -21,7 +21,7 @@ def _ptr(a):
 
 
 class NSAssembler:
-    def __init__(self, x, cells, dofmap, vdeg=1, n_dofs_owned=None, n_dofs_ghost=0, n_cells_owned=None, device=0):
+    def __init__(self, x, cells, dofmap, vdeg=1, n_dofs_owned=None, n_dofs_ghost=0, n_cells_owned=None, device=0, options=None):
         self.lib = _lib.load()
         self.ctx = ctypes.c_void_p()
         rc = self.lib.nsgpu_create(ctypes.byref(self.ctx), device)
@@ -43,6 +43,8 @@ class NSAssembler:
         self.n_owned = n_total - int(n_dofs_ghost) if n_dofs_owned is None else int(n_dofs_owned)
         self.n_ghost = int(n_dofs_ghost)
         self.n_dofs = self.n_owned + self.n_ghost
+        for k, v in (options or {}).items():          # options that must be known before the space is set ("renumber", "renumber_order")
+            self.set_option(k, v)
         self._check(self.lib.nsgpu_set_mesh(self.ctx, self.gdim, x.shape[0], _ptr(x), self.n_cells_owned, self.n_cells_total, _ptr(cells)), "set_mesh")
         self._check(self.lib.nsgpu_set_space(self.ctx, vdeg, _ptr(dofmap), self.n_owned, self.n_ghost), "set_space")
         self.n_cols = self.n_dofs
@@ -235,6 +237,19 @@ class NSAssembler:
         self._check(self.lib.nsgpu_get_values(self.ctx, _ptr(out)), "get_values")
         return out
 
+    def values_dev(self):
+        """Device pointer of the CSR values in the caller's order (the resident array itself unless the library renumbered)."""
+        p = ctypes.c_void_p()
+        self._check(self.lib.nsgpu_values_dev(self.ctx, ctypes.byref(p)), "values_dev")
+        return p
+
+    def get_value_range(self, start, n, vals_dev=None):
+        """CSR values [start, start + n) of the resident matrix (rows of huge matrices without fetching 16 GB)."""
+        p = self.values_dev() if vals_dev is None else vals_dev
+        out = np.empty(int(n))
+        self.d2h(out, ctypes.c_void_p(p.value + 8 * int(start)))
+        return out
+
     def timers(self):
         ms = (ctypes.c_double * 8)()
         self._check(self.lib.nsgpu_timers(self.ctx, ms, 8), "timers")
@@ -243,6 +258,9 @@ class NSAssembler:
 
     def last_kernel_name(self):
         return self.lib.nsgpu_last_kernel_name(self.ctx).decode()
+
+    def last_spmv_name(self):
+        return self.lib.nsgpu_last_spmv_name(self.ctx).decode()
 
     def launch_count(self):
         return int(self.lib.nsgpu_launch_count(self.ctx))

@@ -217,6 +217,37 @@ int k_bc_diagonal_launch(nsgpu_ctx* ctx) {
   return NSGPU_OK;
 }
 
+// NaN / Inf guard on a freshly assembled vector (PETSc's SNES stops with DIVERGED_FNORM_NAN; here the
+// assembly call itself reports it).  All ranks see the same verdict: the flag is summed over the communicator.
+__global__ void k_nonfinite(int64_t n, const double* __restrict__ v, int* flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && !isfinite(v[i])) *flag = 1;
+}
+
+// sync_now = false (device-pointer entry points, which stay asynchronous): the scan is queued and the sticky flag is
+// read by the next nsgpu_sync / host-vector call
+int check_finite_impl(nsgpu_ctx* ctx, const double* d_v, int64_t n, const char* what, bool sync_now) {
+  cudaStream_t s = ctx->stream;
+  if (!ctx->d_nonfinite) {
+    NS_CUDA(ctx, cudaMalloc(&ctx->d_nonfinite, 2 * sizeof(double)));
+    NS_CUDA(ctx, cudaMemsetAsync(ctx->d_nonfinite, 0, 2 * sizeof(double), s));
+  }
+  if (d_v && n > 0) {
+    k_nonfinite<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, d_v, ctx->d_nonfinite);
+    ctx->launches += 1;
+  }
+  if (!sync_now) return NSGPU_OK;
+  int flag = 0;
+  NS_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  if (flag) {
+    NS_CUDA(ctx, cudaMemsetAsync(ctx->d_nonfinite, 0, 2 * sizeof(double), s));
+    set_error(ctx, std::string(what) + ": non-finite entries (NaN / Inf) in the assembled vector");
+    return NSGPU_ENONFINITE;
+  }
+  return NSGPU_OK;
+}
+
 // d_xin: n_cols state (halo already refreshed).  d_Fout: n_cols residual (zeroed here; owned part meaningful).
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
   cudaStream_t s = ctx->stream;

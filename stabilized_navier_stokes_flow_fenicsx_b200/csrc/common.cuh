@@ -111,6 +111,8 @@ struct nsgpu_ctx {
   bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
   double* d_x_last = nullptr;
   int64_t fused_hits = 0;
+  int check_finite = 1;    // scan the owned residual entries for NaN / Inf after every residual assembly (status NSGPU_ENONFINITE)
+  int* d_nonfinite = nullptr;
   int spmv_blocks = 5;     // vertex-blocked SpMV: resident 256-thread CTAs per SM the kernel is compiled for (4, 5 or 6)
   int stream_chunks = 16;  // tile chunks of the streamed host path
   int stream_host = 1; // host-vector J+F entry point: overlap H2D(x) / tile chunks / D2H(F) on three streams when the pipelined kernel applies
@@ -120,6 +122,7 @@ struct nsgpu_ctx {
   cudaEvent_t tev[2] = {nullptr, nullptr};   // user timer (nsgpu_timer_start/stop)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t launches = 0;
+  const char* last_spmv = "none";     // which MatMult kernel the last product used (nsgpu_last_spmv_name)
   const char* last_kernel = "none";   // which assembly variant the last call used (nsgpu_last_kernel_name)
 
   // multi-GPU
@@ -163,6 +166,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int build_pattern_impl(nsgpu_ctx* ctx);
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);
 int k_bc_diagonal_launch(nsgpu_ctx* ctx);
+int check_finite_impl(nsgpu_ctx* ctx, const double* d_v, int64_t n, const char* what, bool sync_now);
 int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y);
 int halo_forward(nsgpu_ctx* ctx, double* d_v);
 int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);

@@ -212,8 +212,16 @@ extern "C" int nsgpu_set_halo(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_
   if ((rc = dev_alloc(ctx, &h.d_recv_idx, nr))) return rc;
   if ((rc = dev_alloc(ctx, &h.d_send_buf, ns))) return rc;
   if ((rc = dev_alloc(ctx, &h.d_recv_buf, nr))) return rc;
-  if (ns) NS_CUDA(ctx, cudaMemcpy(h.d_send_idx, send_idx, sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
-  if (nr) NS_CUDA(ctx, cudaMemcpy(h.d_recv_idx, recv_idx, sizeof(int32_t) * nr, cudaMemcpyHostToDevice));
+  // index lists arrive in the caller's numbering; below the ABI everything is internal (renumber.cu)
+  std::vector<int32_t> si(send_idx, send_idx + ns), ri(recv_idx, recv_idx + nr);
+  for (int64_t k = 0; k < ns; ++k) NS_REQUIRE(ctx, si[k] >= 0 && si[k] < ctx->n_cols, "set_halo: send index out of range");
+  for (int64_t k = 0; k < nr; ++k) NS_REQUIRE(ctx, ri[k] >= 0 && ri[k] < ctx->n_cols, "set_halo: receive index out of range");
+  if (ctx->d_perm) {
+    for (auto& d : si) if (d < ctx->n_dofs) d = ctx->h_perm[d];
+    for (auto& d : ri) if (d < ctx->n_dofs) d = ctx->h_perm[d];
+  }
+  if (ns) NS_CUDA(ctx, cudaMemcpy(h.d_send_idx, si.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
+  if (nr) NS_CUDA(ctx, cudaMemcpy(h.d_recv_idx, ri.data(), sizeof(int32_t) * nr, cudaMemcpyHostToDevice));
   return NSGPU_OK;
 }
 
@@ -233,6 +241,12 @@ extern "C" int nsgpu_set_row_exchange(nsgpu_ctx* ctx, int n_neigh, const int32_t
   if ((rc = dev_alloc(ctx, &r.d_recv_pos, nr))) return rc;
   if ((rc = dev_alloc(ctx, &r.d_send_buf, ns))) return rc;
   if ((rc = dev_alloc(ctx, &r.d_recv_buf, nr))) return rc;
+  if (ctx->d_perm) {   // CSR positions of the caller-order pattern -> positions in the internal value array
+    NS_REQUIRE(ctx, ctx->pattern_built, "set_row_exchange: call build_pattern first");
+    if ((rc = translate_positions(ctx, ns, send_pos, r.d_send_pos))) return rc;
+    if ((rc = translate_positions(ctx, nr, recv_pos, r.d_recv_pos))) return rc;
+    return NSGPU_OK;
+  }
   if (ns) NS_CUDA(ctx, cudaMemcpy(r.d_send_pos, send_pos, sizeof(int64_t) * ns, cudaMemcpyHostToDevice));
   if (nr) NS_CUDA(ctx, cudaMemcpy(r.d_recv_pos, recv_pos, sizeof(int64_t) * nr, cudaMemcpyHostToDevice));
   return NSGPU_OK;

@@ -63,6 +63,50 @@ static int same_state(nsgpu_ctx* ctx, bool* same) {
   *same = flag == 0;
   return NSGPU_OK;
 }
+
+// ---- internal numbering (renumber.cu): vectors / values cross the ABI in the CALLER's numbering ----
+static inline bool permuted(const nsgpu_ctx* ctx) { return ctx->d_perm != nullptr; }
+
+// host vector (caller order, n entries, n <= n_dofs) -> internal device vector
+static int vec_in(nsgpu_ctx* ctx, const double* host, double* d_dst, int64_t n) {
+  cudaStream_t s = ctx->stream;
+  if (!permuted(ctx)) {
+    NS_CUDA(ctx, cudaMemcpyAsync(d_dst, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    return NSGPU_OK;
+  }
+  int rc = perm_work(ctx);
+  if (rc) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_px, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  return perm_in(ctx, ctx->d_px, d_dst, n, n);
+}
+
+// internal device vector -> host vector (caller order, n entries)
+static int vec_out(nsgpu_ctx* ctx, const double* d_src, double* host, int64_t n) {
+  cudaStream_t s = ctx->stream;
+  if (!permuted(ctx)) {
+    NS_CUDA(ctx, cudaMemcpyAsync(host, d_src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    return NSGPU_OK;
+  }
+  int rc = perm_work(ctx);
+  if (rc) return rc;
+  if ((rc = perm_out(ctx, d_src, ctx->d_pF, n, n))) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_pF, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  return NSGPU_OK;
+}
+
+// resident CSR values -> host array in the caller's CSR order
+static int vals_out(nsgpu_ctx* ctx, double* host) {
+  cudaStream_t s = ctx->stream;
+  const double* src = ctx->d_vals;
+  if (permuted(ctx)) {
+    int rc = caller_vals_buffer(ctx);
+    if (rc) return rc;
+    if ((rc = export_values(ctx, ctx->d_vals_c))) return rc;
+    src = ctx->d_vals_c;
+  }
+  NS_CUDA(ctx, cudaMemcpyAsync(host, src, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, s));
+  return NSGPU_OK;
+}
 }  // namespace nsgpu
 
 extern "C" {
@@ -106,6 +150,8 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
   krylov_free(ctx);
+  renumber_free(ctx);
+  cudaFree(ctx->d_nonfinite);
   cudaFree(ctx->d_x_last);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -129,6 +175,13 @@ int nsgpu_set_mesh(nsgpu_ctx* ctx, int gdim, int64_t n_nodes, const double* x, i
   NS_REQUIRE(ctx, x && x_dofmap && n_nodes > 0 && n_cells_owned >= 0 && n_cells_total >= n_cells_owned, "set_mesh: bad sizes or NULL arrays");
   ctx->gdim = gdim; ctx->n_nodes = n_nodes; ctx->n_cells_owned = n_cells_owned; ctx->n_cells_total = n_cells_total;
   ctx->pattern_built = false;
+  for (int k = 0; k < 3; ++k) { ctx->bbox_lo[k] = x[k]; ctx->bbox_hi[k] = x[k]; }
+  for (int64_t i = 1; i < n_nodes; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const double v = x[3 * i + k];
+      if (v < ctx->bbox_lo[k]) ctx->bbox_lo[k] = v;
+      if (v > ctx->bbox_hi[k]) ctx->bbox_hi[k] = v;
+    }
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_x, n_nodes * 3))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_cells, n_cells_total * (gdim + 1)))) return rc;
@@ -165,7 +218,9 @@ int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_d
   NS_CUDA(ctx, cudaMemset(ctx->d_bc_marker, 0, ctx->n_dofs));
   NS_CUDA(ctx, cudaMemset(ctx->d_bc_value, 0, sizeof(double) * ctx->n_dofs));
   NS_CUDA(ctx, cudaMemset(ctx->d_bc_mult, 0, sizeof(int32_t) * ctx->n_dofs));
-  return NSGPU_OK;
+  // internal vertex-blocked numbering for the P1-P1 tetrahedron space when the caller's is not (renumber.cu); from here on
+  // ctx->d_dofmap and everything derived from it live in the internal numbering
+  return renumber_build(ctx);
 }
 
 int nsgpu_set_form(nsgpu_ctx* ctx, int flavour, double nu, double Ci, double alpha, double sp, double beta) {
@@ -190,8 +245,9 @@ int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr, const int32_t
   for (int b = 0; b < n_bc; ++b) {
     NS_REQUIRE(ctx, bc_ptr[b + 1] >= bc_ptr[b], "set_bcs: bc_ptr must be non-decreasing");
     for (int64_t k = bc_ptr[b]; k < bc_ptr[b + 1]; ++k) {
-      const int32_t d = bc_dofs[k];
+      int32_t d = bc_dofs[k];
       NS_REQUIRE(ctx, d >= 0 && d < ctx->n_dofs, "set_bcs: dof index out of range");
+      if (permuted(ctx)) d = ctx->h_perm[d];
       marker[d] = 1;
       value[d] = bc_vals[k];   // list order: the last DirichletBC object holding the dof wins
       mult[d] += 1;
@@ -212,8 +268,14 @@ int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, co
   for (int64_t k = 0; k < n; ++k) {
     NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_dofs && cols[k] >= 0 && cols[k] < ctx->n_cols, "add_pattern_entries: index out of range");
   }
+  const size_t at = ctx->extra_rows.size();
   ctx->extra_rows.insert(ctx->extra_rows.end(), rows, rows + n);
   ctx->extra_cols.insert(ctx->extra_cols.end(), cols, cols + n);
+  if (permuted(ctx))
+    for (int64_t k = 0; k < n; ++k) {
+      ctx->extra_rows[at + k] = ctx->h_perm[rows[k]];
+      if (cols[k] < ctx->n_dofs) ctx->extra_cols[at + k] = ctx->h_perm[cols[k]];
+    }
   ctx->pattern_built = false;
   return NSGPU_OK;
 }
@@ -253,12 +315,19 @@ int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* star
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built, "get_rows: call build_pattern first");
   NS_REQUIRE(ctx, n >= 0 && (n == 0 || (rows && ptr_out)), "get_rows: NULL arrays");
+  const int64_t* d_ip = ctx->d_indptr;
+  const int32_t* d_ix = ctx->d_indices;
+  if (permuted(ctx)) {
+    int rc = ensure_caller_pattern(ctx);
+    if (rc) return rc;
+    d_ip = ctx->d_indptr_c; d_ix = ctx->d_indices_c;
+  }
   std::vector<int64_t> b(n), e(n);
   ptr_out[0] = 0;
   for (int64_t k = 0; k < n; ++k) {
     NS_REQUIRE(ctx, rows[k] >= 0 && rows[k] < ctx->n_rows, "get_rows: row out of range");
     int64_t be[2];
-    NS_CUDA(ctx, cudaMemcpy(be, ctx->d_indptr + rows[k], 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    NS_CUDA(ctx, cudaMemcpy(be, d_ip + rows[k], 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     b[k] = be[0]; e[k] = be[1];
     if (start_out) start_out[k] = be[0];
     ptr_out[k + 1] = ptr_out[k] + (be[1] - be[0]);
@@ -266,7 +335,7 @@ int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* star
   if (!idx_out) return NSGPU_OK;   // size query
   NS_REQUIRE(ctx, idx_capacity >= ptr_out[n], "get_rows: idx_out too small");
   for (int64_t k = 0; k < n; ++k)
-    if (e[k] > b[k]) NS_CUDA(ctx, cudaMemcpy(idx_out + ptr_out[k], ctx->d_indices + b[k], sizeof(int32_t) * (e[k] - b[k]), cudaMemcpyDeviceToHost));
+    if (e[k] > b[k]) NS_CUDA(ctx, cudaMemcpy(idx_out + ptr_out[k], d_ix + b[k], sizeof(int32_t) * (e[k] - b[k]), cudaMemcpyDeviceToHost));
   return NSGPU_OK;
 }
 
@@ -278,6 +347,8 @@ int nsgpu_build_pattern(nsgpu_ctx* ctx, int64_t* nnz_out) {
   NS_CUDA(ctx, cudaEventCreate(&a));
   NS_CUDA(ctx, cudaEventCreate(&b));
   cudaEventRecord(a, ctx->stream);
+  cudaFree(ctx->d_indptr_c); cudaFree(ctx->d_indices_c); cudaFree(ctx->d_vals_c);
+  ctx->d_indptr_c = nullptr; ctx->d_indices_c = nullptr; ctx->d_vals_c = nullptr; ctx->caller_pattern_built = false;
   int rc = build_pattern_impl(ctx);
   cudaEventRecord(b, ctx->stream);
   cudaEventSynchronize(b);
@@ -309,8 +380,15 @@ int nsgpu_get_pattern(nsgpu_ctx* ctx, int64_t* indptr, int32_t* indices) {
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built, "get_pattern: call build_pattern first");
   NS_REQUIRE(ctx, indptr && indices, "get_pattern: NULL output");
-  NS_CUDA(ctx, cudaMemcpy(indptr, ctx->d_indptr, sizeof(int64_t) * (ctx->n_rows + 1), cudaMemcpyDeviceToHost));
-  if (ctx->nnz) NS_CUDA(ctx, cudaMemcpy(indices, ctx->d_indices, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
+  const int64_t* d_ip = ctx->d_indptr;
+  const int32_t* d_ix = ctx->d_indices;
+  if (permuted(ctx)) {   // the caller's numbering: rows in its order, sorted local columns (dolfinx la::SparsityPattern order)
+    int rc = ensure_caller_pattern(ctx);
+    if (rc) return rc;
+    d_ip = ctx->d_indptr_c; d_ix = ctx->d_indices_c;
+  }
+  NS_CUDA(ctx, cudaMemcpy(indptr, d_ip, sizeof(int64_t) * (ctx->n_rows + 1), cudaMemcpyDeviceToHost));
+  if (ctx->nnz) NS_CUDA(ctx, cudaMemcpy(indices, d_ix, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
   return NSGPU_OK;
 }
 
@@ -325,8 +403,22 @@ int nsgpu_jacobian_residual_dev(nsgpu_ctx* ctx, double* x_local_dev, int want_ja
   int rc = ready(ctx);
   if (rc) return rc;
   NS_REQUIRE(ctx, x_local_dev && (want_jacobian || F_local_dev), "jacobian_residual_dev: nothing to do / NULL state");
-  if ((rc = halo_forward(ctx, x_local_dev))) return rc;     // x.ghostUpdate(INSERT, FORWARD)
-  return assemble_impl(ctx, x_local_dev, want_jacobian != 0, F_local_dev != nullptr, F_local_dev);
+  if (!permuted(ctx)) {
+    if ((rc = halo_forward(ctx, x_local_dev))) return rc;     // x.ghostUpdate(INSERT, FORWARD)
+    rc = assemble_impl(ctx, x_local_dev, want_jacobian != 0, F_local_dev != nullptr, F_local_dev);
+    if (rc == NSGPU_OK && F_local_dev && ctx->check_finite) rc = check_finite_impl(ctx, F_local_dev, ctx->n_owned, "residual", false);
+    return rc;
+  }
+  // caller-ordered device vectors: one gather pass in, one out
+  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  if (ctx->nranks > 1 && (rc = perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_dofs, ctx->n_cols))) return rc;   // the refreshed ghost entries
+  if ((rc = assemble_impl(ctx, ctx->d_xvec, want_jacobian != 0, F_local_dev != nullptr, ctx->d_F))) return rc;
+  if (F_local_dev) {
+    if (ctx->check_finite && (rc = check_finite_impl(ctx, ctx->d_F, ctx->n_owned, "residual", false))) return rc;
+    if ((rc = perm_out(ctx, ctx->d_F, F_local_dev, ctx->n_dofs, ctx->n_dofs))) return rc;
+  }
+  return NSGPU_OK;
 }
 
 int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals, double* F_local) {
@@ -335,7 +427,7 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
   if (rc) return rc;
   NS_REQUIRE(ctx, x_local != nullptr, "x_local is NULL");
   cudaStream_t s = ctx->stream;
-  if (F_local && ctx->stream_host) {
+  if (F_local && ctx->stream_host && !permuted(ctx)) {
     // single rank, factorised kernel: H2D of x, the tile chunks and D2H of F overlap on three streams (p1tet.cu)
     rc = p1tet_assemble_streamed(ctx, x_local, F_local);
     if (rc < 0) return rc;
@@ -344,19 +436,21 @@ int nsgpu_jacobian_residual(nsgpu_ctx* ctx, const double* x_local, double* vals,
       if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
       if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
       NS_CUDA(ctx, cudaStreamSynchronize(s));
+      if (ctx->check_finite && (rc = check_finite_impl(ctx, ctx->d_F, ctx->n_owned, "residual", true))) return rc;
       return elapsed(ctx, 0);
     }
   }
-  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = vec_in(ctx, x_local, ctx->d_xvec, ctx->n_dofs))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   // the Jacobian is always assembled; vals == NULL keeps it on the device (MatShell use with nsgpu_spmv)
   const bool want_F = F_local != nullptr;
   const bool want_J = true;
   if ((rc = assemble_impl(ctx, ctx->d_xvec, want_J, want_F, ctx->d_F))) return rc;
-  if (want_F) NS_CUDA(ctx, cudaMemcpyAsync(F_local, ctx->d_F, sizeof(double) * ctx->n_dofs, cudaMemcpyDeviceToHost, s));
-  if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  if (want_F && (rc = vec_out(ctx, ctx->d_F, F_local, ctx->n_dofs))) return rc;
+  if (vals && (rc = vals_out(ctx, vals))) return rc;
   if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
+  if (want_F && ctx->check_finite && (rc = check_finite_impl(ctx, ctx->d_F, ctx->n_owned, "residual", true))) return rc;
   return elapsed(ctx, 0);
 }
 
@@ -367,11 +461,12 @@ int nsgpu_residual(nsgpu_ctx* ctx, const double* x_local, double* F_local) {
   NS_REQUIRE(ctx, x_local && F_local, "residual: NULL argument");
   if (ctx->fuse_fj) return nsgpu_jacobian_residual(ctx, x_local, nullptr, F_local);   // J stays resident for the nsgpu_jacobian call that follows
   cudaStream_t s = ctx->stream;
-  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = vec_in(ctx, x_local, ctx->d_xvec, ctx->n_dofs))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   if ((rc = assemble_impl(ctx, ctx->d_xvec, false, true, ctx->d_F))) return rc;
-  NS_CUDA(ctx, cudaMemcpyAsync(F_local, ctx->d_F, sizeof(double) * ctx->n_dofs, cudaMemcpyDeviceToHost, s));
+  if ((rc = vec_out(ctx, ctx->d_F, F_local, ctx->n_dofs))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
+  if (ctx->check_finite && (rc = check_finite_impl(ctx, ctx->d_F, ctx->n_owned, "residual", true))) return rc;
   return elapsed(ctx, 1);
 }
 
@@ -381,18 +476,18 @@ int nsgpu_jacobian(nsgpu_ctx* ctx, const double* x_local, double* vals) {
   if (rc) return rc;
   NS_REQUIRE(ctx, x_local != nullptr, "x_local is NULL");
   cudaStream_t s = ctx->stream;
-  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
+  if ((rc = vec_in(ctx, x_local, ctx->d_xvec, ctx->n_dofs))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   bool same = false;
   if (ctx->fuse_fj && (rc = same_state(ctx, &same))) return rc;
   if (same) {   // assembled by the residual call at this very state
     ctx->fused_hits += 1;
-    if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+    if (vals && (rc = vals_out(ctx, vals))) return rc;
     NS_CUDA(ctx, cudaStreamSynchronize(s));
     return NSGPU_OK;
   }
   if ((rc = assemble_impl(ctx, ctx->d_xvec, true, false, ctx->d_F))) return rc;
-  if (vals) NS_CUDA(ctx, cudaMemcpyAsync(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+  if (vals && (rc = vals_out(ctx, vals))) return rc;
   if (ctx->fuse_fj && (rc = remember_state(ctx))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return elapsed(ctx, 0);
@@ -403,8 +498,14 @@ int nsgpu_spmv_dev(nsgpu_ctx* ctx, double* x_local_dev, double* y_owned_dev) {
   NS_REQUIRE(ctx, ctx->pattern_built, "spmv: call build_pattern first");
   NS_REQUIRE(ctx, x_local_dev && y_owned_dev, "spmv: NULL argument");
   int rc;
-  if ((rc = halo_forward(ctx, x_local_dev))) return rc;
-  return spmv_impl(ctx, x_local_dev, y_owned_dev);
+  if (!permuted(ctx)) {
+    if ((rc = halo_forward(ctx, x_local_dev))) return rc;
+    return spmv_impl(ctx, x_local_dev, y_owned_dev);
+  }
+  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
+  if ((rc = spmv_impl(ctx, ctx->d_xvec, ctx->d_y))) return rc;
+  return perm_out(ctx, ctx->d_y, y_owned_dev, ctx->n_owned, ctx->n_owned);
 }
 
 int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned) {
@@ -412,11 +513,11 @@ int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned) {
   NS_REQUIRE(ctx, ctx->pattern_built, "spmv: call build_pattern first");
   NS_REQUIRE(ctx, x_local && y_owned, "spmv: NULL argument");
   cudaStream_t s = ctx->stream;
-  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_local, sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice, s));
   int rc;
+  if ((rc = vec_in(ctx, x_local, ctx->d_xvec, ctx->n_dofs))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   if ((rc = spmv_impl(ctx, ctx->d_xvec, ctx->d_y))) return rc;
-  NS_CUDA(ctx, cudaMemcpyAsync(y_owned, ctx->d_y, sizeof(double) * ctx->n_owned, cudaMemcpyDeviceToHost, s));
+  if ((rc = vec_out(ctx, ctx->d_y, y_owned, ctx->n_owned))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return elapsed(ctx, 2);
 }
@@ -427,7 +528,14 @@ int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_d
   NS_REQUIRE(ctx, ctx->pattern_built, "tfqmr: call build_pattern and assemble a Jacobian first");
   NS_REQUIRE(ctx, b_owned_dev && x_local_dev, "tfqmr: NULL argument");
   NS_REQUIRE(ctx, max_it >= 0 && rtol >= 0.0 && atol >= 0.0, "tfqmr: negative tolerance or iteration limit");
-  return tfqmr_impl(ctx, b_owned_dev, x_local_dev, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
+  if (!permuted(ctx)) return tfqmr_impl(ctx, b_owned_dev, x_local_dev, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
+  // the whole solve runs in the internal numbering: b in, x in (unless zero guess), x out
+  int rc;
+  if ((rc = perm_in(ctx, b_owned_dev, ctx->d_F, ctx->n_owned, ctx->n_owned))) return rc;
+  if (zero_guess) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols, ctx->stream));
+  else if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  if ((rc = tfqmr_impl(ctx, ctx->d_F, ctx->d_xvec, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out))) return rc;
+  return perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_dofs, ctx->n_cols);
 }
 
 int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double rtol, double atol, int max_it, int pc, int zero_guess,
@@ -438,12 +546,13 @@ int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double r
   NS_REQUIRE(ctx, max_it >= 0 && rtol >= 0.0 && atol >= 0.0, "tfqmr: negative tolerance or iteration limit");
   cudaStream_t s = ctx->stream;
   // d_F holds b, d_xvec the iterate (both n_cols long)
-  NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_F, b_owned, sizeof(double) * ctx->n_owned, cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = vec_in(ctx, b_owned, ctx->d_F, ctx->n_owned))) return rc;
   NS_CUDA(ctx, cudaMemsetAsync(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols, s));
-  if (!zero_guess) NS_CUDA(ctx, cudaMemcpyAsync(ctx->d_xvec, x_owned, sizeof(double) * ctx->n_owned, cudaMemcpyHostToDevice, s));
-  int rc = tfqmr_impl(ctx, ctx->d_F, ctx->d_xvec, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
+  if (!zero_guess && (rc = vec_in(ctx, x_owned, ctx->d_xvec, ctx->n_owned))) return rc;
+  rc = tfqmr_impl(ctx, ctx->d_F, ctx->d_xvec, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out);
   if (rc != NSGPU_OK) return rc;
-  NS_CUDA(ctx, cudaMemcpyAsync(x_owned, ctx->d_xvec, sizeof(double) * ctx->n_owned, cudaMemcpyDeviceToHost, s));
+  if ((rc = vec_out(ctx, ctx->d_xvec, x_owned, ctx->n_owned))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return NSGPU_OK;
 }
@@ -464,6 +573,14 @@ int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
   if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built && vals, "set_values: no pattern or NULL values");
+  if (permuted(ctx)) {
+    int rc = caller_vals_buffer(ctx);
+    if (rc) return rc;
+    NS_CUDA(ctx, cudaMemcpy(ctx->d_vals_c, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
+    if ((rc = import_values(ctx, ctx->d_vals_c))) return rc;
+    NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NSGPU_OK;
+  }
   NS_CUDA(ctx, cudaMemcpy(ctx->d_vals, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
   return NSGPU_OK;
 }
@@ -471,20 +588,29 @@ int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
 int nsgpu_get_values(nsgpu_ctx* ctx, double* vals) {
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built && vals, "get_values: no pattern or NULL output");
+  int rc = vals_out(ctx, vals);
+  if (rc) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  NS_CUDA(ctx, cudaMemcpy(vals, ctx->d_vals, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost));
   return NSGPU_OK;
 }
 
 int nsgpu_values_dev(nsgpu_ctx* ctx, double** vals_dev) {
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, ctx->pattern_built && vals_dev, "values_dev: no pattern");
+  if (permuted(ctx)) {   // a copy in the caller's CSR order (refreshed by every call)
+    int rc = caller_vals_buffer(ctx);
+    if (rc) return rc;
+    if ((rc = export_values(ctx, ctx->d_vals_c))) return rc;
+    *vals_dev = ctx->d_vals_c;
+    return NSGPU_OK;
+  }
   *vals_dev = ctx->d_vals;
   return NSGPU_OK;
 }
 
 int nsgpu_sync(nsgpu_ctx* ctx) {
   NS_ENTER(ctx);
+  if (ctx->check_finite && ctx->d_nonfinite) return check_finite_impl(ctx, nullptr, 0, "a device-pointer residual assembly since the last sync", true);
   NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NSGPU_OK;
 }
@@ -528,6 +654,7 @@ int nsgpu_host_alloc_pinned(int64_t bytes, void** out) {
 int nsgpu_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? NSGPU_OK : NSGPU_ECUDA; }
 
 const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+const char* nsgpu_last_spmv_name(const nsgpu_ctx* ctx) { return ctx ? ctx->last_spmv : "none"; }
 
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
   if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
@@ -550,6 +677,8 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {
     ctx->pipe = value != 0;
+  } else if (!strcmp(name, "check_finite")) {
+    ctx->check_finite = value != 0;
   } else if (!strcmp(name, "renumber")) {
     NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: renumber must be 0 (never), 1 (when the caller's numbering is not vertex-blocked) or 2 (always)");
     NS_REQUIRE(ctx, ctx->d_dofmap == nullptr, "set_option: renumber must be set before set_space");

@@ -32,10 +32,13 @@ int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
   if (ctx->kernel_sel != NSGPU_KERNEL_GENERIC && p1tet_spmv(ctx, d_x, d_y)) {
     // vertex-blocked P1-P1 matrix: one column index per 4x4 block (p1tet.cu)
-  } else
+    ctx->last_spmv = "spmv_block4";
+  } else {
+  ctx->last_spmv = "spmv_csr";
   if (avg > 48) k_spmv<16><<<(unsigned)ceil_div(n * 16, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
   else if (avg > 24) k_spmv<8><<<(unsigned)ceil_div(n * 8, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
   else k_spmv<4><<<(unsigned)ceil_div(n * 4, bs), bs, 0, s>>>(n, ctx->d_indptr, ctx->d_indices, ctx->d_vals, d_x, d_y);
+  }
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());

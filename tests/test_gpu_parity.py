@@ -123,24 +123,58 @@ def test_lifting_with_state_off_the_dirichlet_values(oracle):
     asm.close()
 
 
-def test_arbitrary_dof_numbering(oracle):
-    """dolfinx renumbers dofs (reverse Cuthill-McKee): nothing may depend on entity-contiguous numbering."""
+@pytest.mark.parametrize("order", [2, 1])
+def test_arbitrary_dof_numbering(oracle, order):
+    """dolfinx renumbers dofs (reverse Cuthill-McKee) and W.dofmap.list of the mixed space has block size 1
+    (NavierStokes/NavierStokesChannelFlow.py:128-129): nothing at the ABI may depend on a vertex-blocked numbering.
+    The library renumbers internally (Morton order of the vertices, or leader-dof order) and the FAST kernels must run;
+    pattern, values, residual, MatMult and the Krylov solve come back in the caller's numbering."""
     m, sp, w, bcs, fk = _case("duct_p1_re70")
     perm = np.random.default_rng(3).permutation(sp.n_dofs).astype(np.int32)
     dofmap = perm[sp.dofmap]
     w2 = np.empty_like(w); w2[perm] = w
+    w2 += 0.01 * np.random.default_rng(8).standard_normal(sp.n_dofs)        # off the Dirichlet values: lifting active
     bcs2 = [(perm[d], v) for d, v in bcs]
     form = oracle.Form(gdim=3, vdeg=1, **fk)
     marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs2], [b[1] for b in bcs2])
     indptr, indices = oracle.build_pattern(dofmap, sp.n_dofs)
     vals = oracle.assemble_jacobian(form, m.x, m.cells, dofmap, w2, indptr, indices, marker, mult)
-    asm = NSAssembler(m.x, m.cells, dofmap, vdeg=1)
+    F = oracle.assemble_residual(form, m.x, m.cells, dofmap, w2, marker, value)
+    oracle.set_bc(F, [b[0] for b in bcs2], [b[1] for b in bcs2], w2)
+    asm = NSAssembler(m.x, m.cells, dofmap, vdeg=1, options={"renumber_order": order})
     asm.set_form(**fk); asm.set_bcs(bcs2)
+    asm.set_option("kernel", 2)                                               # fails loudly if the factorised kernels do not apply
     gp, gi = asm.create_matrix()
     np.testing.assert_array_equal(gp, indptr)
     np.testing.assert_array_equal(gi, indices)
-    gv = asm.jacobian(w2)
+    gv, gF = asm.jacobian_residual(w2)
+    assert asm.last_kernel_name() == "p1tet_ws"
     assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
+    assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    assert np.abs(asm.residual(w2) - F).max() <= RTOL * np.abs(F).max()
+    assert np.abs(asm.jacobian(w2) - vals).max() <= RTOL * np.abs(vals).max()
+    xv = np.random.default_rng(1).standard_normal(sp.n_dofs)
+    y = asm.mult(xv)
+    assert asm.last_spmv_name() == "spmv_block4"
+    yo = oracle.spmv(indptr, indices, vals, xv)
+    assert np.abs(y - yo).max() <= RTOL * np.abs(yo).max()
+    # device-pointer variants see the caller's numbering too
+    x_dev, F_dev, y_dev = asm.dev_alloc(8 * asm.n_cols), asm.dev_alloc(8 * asm.n_cols), asm.dev_alloc(8 * asm.n_cols)
+    asm.h2d(x_dev, w2)
+    asm.jacobian_residual_dev(x_dev, True, F_dev)
+    Fh = np.zeros(sp.n_dofs); asm.d2h(Fh, F_dev)
+    assert np.abs(Fh - F).max() <= RTOL * np.abs(F).max()
+    asm.h2d(x_dev, xv); asm.spmv_dev(x_dev, y_dev)
+    yh = np.zeros(sp.n_dofs); asm.d2h(yh, y_dev)
+    assert np.abs(yh - yo).max() <= RTOL * np.abs(yo).max()
+    # values round trip in the caller's CSR order, and the Krylov solve on them
+    np.testing.assert_array_equal(asm.get_values(), gv)
+    asm.set_values(2.0 * gv)
+    assert np.abs(asm.mult(xv) - 2.0 * yo).max() <= RTOL * 2 * np.abs(yo).max()
+    asm.set_values(gv)
+    b = oracle.spmv(indptr, indices, vals, xv)
+    xs, info = asm.tfqmr(b, rtol=1e-12, max_it=2000)
+    assert np.linalg.norm(oracle.spmv(indptr, indices, vals, xs) - b) <= 1e-9 * np.linalg.norm(b)
     asm.close()
 
 
@@ -347,3 +381,28 @@ def test_two_gpu_halo_and_row_exchange():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29613", os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_nonfinite_residual_is_reported():
+    """a diverged state must not pass silently -- the assembly call returns NSGPU_ENONFINITE."""
+    from stabilized_navier_stokes_flow_fenicsx_b200._lib import NsgpuError
+    m, sp, w, bcs, fk = _case("duct_p1")
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix(fetch=False)
+    asm.residual(w)                                   # a finite state passes
+    w2 = w.copy(); w2[sp.n_dofs // 2] = np.nan
+    with pytest.raises(NsgpuError, match="non-finite"):
+        asm.residual(w2)
+    with pytest.raises(NsgpuError, match="non-finite"):
+        asm.jacobian_residual(w2)
+    x_dev, F_dev = asm.dev_alloc(8 * asm.n_cols), asm.dev_alloc(8 * asm.n_cols)
+    asm.h2d(x_dev, w2)
+    asm.jacobian_residual_dev(x_dev, True, F_dev)    # asynchronous: reported by the next sync
+    with pytest.raises(NsgpuError, match="non-finite"):
+        asm.sync()
+    asm.h2d(x_dev, w)
+    asm.jacobian_residual_dev(x_dev, True, F_dev)
+    asm.sync()
+    asm.set_option("check_finite", 0)
+    asm.residual(w2)
+    asm.close()
