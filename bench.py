@@ -32,9 +32,13 @@ NU, CI = 0.1, 36.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the assembly kernel, one launch, from the committed ncu --set full capture
 # (default kernel options, 1 GPU): 6.03 GB read + 16.46 GB written, against 21.0 GB algorithmic (the pipelined kernel reads
 # one vertex list per tile instead of eight indices per incidence, which removed ~9 GB of index traffic).
-NCU_TRAFFIC = {"L": (22.49e9, "profiles/r1c_ncu_full_L_p1tet_pipe.txt")}
-# executed fp64 work of the assembly kernel from the same capture: 2*DFMA + DADD + DMUL thread instructions per cell
-FLOP_PER_CELL = 5426
+# Keyed by (workload, kernel name): the figures are only quoted when the run used that kernel on that workload on 1 GPU.
+NCU_PROFILE = {
+    ("L", "p1tet_pipe"): {"traffic": 22.49e9, "flop_per_cell": 5426, "source": "profiles/r1c_ncu_full_L_p1tet_pipe.txt"},
+}
+# executed fp64 work of the row-owner kernels per cell when no capture of the exact kernel is on file: 2*DFMA + DADD + DMUL thread
+# instructions, 4 incidences per cell (the algebra is the same code in every variant; DESIGN.md 4.3 derives the count)
+FLOP_PER_CELL_MODEL = 5426
 
 
 def peaks():
@@ -93,31 +97,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- reference arm
-def cpu_sample_run(steps, warmup, n_cross, build_pattern_on_gpu):
-    """Oracle (CPU restatement of the reference algorithm, OpenMP over all host cores) on a bounded slab of
-    the same duct: same cross-section and box size as the GPU workload, fewer boxes along the axis."""
+CPU_SAMPLE_LAYERS = {"L": 6, "M": 40, "S": 40}   # box layers of the duct in the CPU sample: L 589 824 cells, M 600 000, S the whole mesh
+
+
+def cpu_sample_run(steps, warmup, workload):
+    """Oracle (CPU restatement of the reference algorithm, OpenMP over ALL host cores) on a bounded slab of the same duct:
+    same cross-section and box size as the GPU workload, fewer box layers along the axis.  The sample and the thread count
+    do not depend on the number of GPUs or on what the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
     from oracle import oracle
     from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
     cores = oracle.num_threads()
-    # ~0.012 Mcells/s/core for J+F measured on the build box; aim at ~3 s of CPU work per step
-    target_cells = max(6 * n_cross * n_cross * 2, int(0.012e6 * cores * 3.0))
-    n_long = max(2, int(round(target_cells / (6.0 * n_cross * n_cross))))
-    length = 4.0 * n_long / WORKLOADS["L"][1] if n_cross == WORKLOADS["L"][0] else 4.0 * n_long / max(n_long, 1)
+    n_cross, n_long_full = WORKLOADS[workload]
+    n_long = min(CPU_SAMPLE_LAYERS[workload], n_long_full)
+    length = 4.0 * n_long / n_long_full
     m = M.duct_mesh(n_cross, n_long, length=length)
     sp = M.mixed_space(m, 1)
     w, bcs = M.duct_state(sp), M.duct_bcs(sp, length=length)
     marker, value, mult = oracle.bc_arrays(sp.n_dofs, [b[0] for b in bcs], [b[1] for b in bcs])
-    indptr = indices = None
-    if build_pattern_on_gpu:
-        try:
-            from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler
-            asm = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=1)
-            indptr, indices = asm.create_matrix()
-            asm.close()
-        except Exception:
-            indptr = None
-    if indptr is None:
-        indptr, indices = oracle.build_pattern(sp.dofmap, sp.n_dofs)
+    indptr, indices = oracle.build_pattern_c(sp.dofmap, sp.n_dofs)          # create_matrix(): untimed, like the GPU arm's set-up
     form = oracle.Form(0, 3, 1, NU, CI)
     times = []
     for it in range(warmup + steps):
@@ -131,7 +133,7 @@ def cpu_sample_run(steps, warmup, n_cross, build_pattern_on_gpu):
     ms = 1e3 * float(np.mean(times))
     return {"value": m.n_cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "cores": cores, "kind": "port",
             "sample": f"{n_cross}x{n_cross}x{n_long} box slab of the duct ({m.n_cells} cells), oracle J+F incl. CSR insertion by row search, "
-                      f"OpenMP {cores} threads, {len(times)} step(s); restated CPU baseline -- not dolfinx (not installable)",
+                      f"OpenMP {cores} threads, {len(times)} step(s) after {warmup} warm-up; restated CPU baseline -- not dolfinx (not installable)",
             "ms_per_step": ms, "cells": m.n_cells}
 
 
@@ -140,9 +142,9 @@ def run_reference(args):
     if rank != 0:
         return
     n_cross, n_long = WORKLOADS[args.workload]
-    r = cpu_sample_run(args.steps, min(args.warmup, 1), n_cross, build_pattern_on_gpu=True)
+    r = cpu_sample_run(args.steps, args.warmup, args.workload)
     line = {"impl": "reference", "metric": "NS Jacobian+residual assembly throughput", "value": r["value"], "unit": "Mcells/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"structured-tet duct {args.workload} ({n_cross}x{n_cross}x{n_long} boxes, P1-P1 G-metric, nu={NU}); bounded sample: {r['sample']}"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -216,6 +218,7 @@ def run_ours(args):
         step()
         kms.append(asm.last_kernel_ms())
     kernel_ms_avg = comm.max(float(np.mean(kms)))
+    kname = asm.last_kernel_name()                                   # the variant the timed steps ran
 
     # residual only, SpMV
     f_ms = []
@@ -245,7 +248,25 @@ def run_ours(args):
     for _ in range(e2e_steps):
         asm.jacobian_residual(xh, F_out=Fh, fetch_vals=False)
     e2e_ms = comm.max(1e3 * (time.perf_counter() - t0) / e2e_steps)
-    f_checksum = float(np.abs(Fh[: asm.n_owned]).sum())
+    # partition-independent checksums of one assembly (all ranks' owned rows): ||F||_2 and ||J||_F
+    asm.jacobian_residual_dev(x_dev, True, F_dev)
+    f_checksum = asm.norm_dev(F_dev)
+    j_checksum = asm.values_norm()
+    fp64_peak = asm.fp64_peak()                                      # live DFMA micro-benchmark on this GPU
+
+    # AIJ mode: the CSR values come back to (pinned) host memory as well -- what createAIJWithArrays / MatUpdateMPIAIJWithArrays needs
+    e2e_aij_ms = None
+    if not args.no_aij:
+        try:
+            vh = asm.pinned_empty(asm.nnz)
+            asm.jacobian_residual(xh, vals_out=vh, F_out=Fh)
+            comm.barrier()
+            t0 = time.perf_counter()
+            asm.jacobian_residual(xh, vals_out=vh, F_out=Fh)
+            e2e_aij_ms = comm.max(1e3 * (time.perf_counter() - t0))
+        except Exception as ex:                                      # pinned allocation of 8 * nnz bytes can fail on a small host
+            e2e_aij_ms = None
+            aij_note = str(ex)
 
     # what one Newton iterate costs through the SNES callbacks (F then J at the same state, host vectors), with the
     # residual call assembling the Jacobian in the same pass (option fuse_fj) -- and the Krylov iteration on the resident J
@@ -274,7 +295,8 @@ def run_ours(args):
     hbm, how = peaks()
     hbm_total = hbm * world
 
-    default_opts = args.kernel is None and args.ws is None and args.pipe is None
+    prof = NCU_PROFILE.get((args.workload, kname)) if world == 1 else None
+    flop_per_cell = prof["flop_per_cell"] if prof else FLOP_PER_CELL_MODEL
     if rank == 0:
         value = nc_total / (ms_per_step * 1e-3) / 1e6
         achieved = b_jf / (kernel_ms_avg * 1e-3) / 1e9
@@ -286,16 +308,16 @@ def run_ours(args):
                                    f"{ndof_total} dofs, nnz {nnz_total}; P1-P1 G-metric SUPG/PSPG/LSIC, nu={NU}, Ci={CI}; "
                                    f"BCs wall/inlet/outlet; x-slab partition over {world} GPU(s)",
                        "l2": "inputs larger than L2 (no flush needed)" if b_jf / world > 4 * 126e6 else "working set near L2 size: latency-bound case",
-                       "kernel": asm_kernel_name(asm), "setup_s": round(setup_s, 2)},
+                       "kernel": kname, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_total, "unit": "GB/s", "frac": achieved / hbm_total,
-                         "traffic": (NCU_TRAFFIC[args.workload][0] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
-                         "traffic_source": (NCU_TRAFFIC[args.workload][1] if (world == 1 and args.workload in NCU_TRAFFIC and default_opts) else None),
+                         "traffic": prof["traffic"] if prof else None,
+                         "traffic_source": (prof["source"] + " (same kernel, same workload, 1 GPU)") if prof else None,
                          "peak_source": how, "kernel_ms": kernel_ms_avg, "algorithmic_bytes": b_jf,
-                         "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): ncu shows DRAM ~9 %, "
-                                 "fp64 pipe ~38 % busy, DRAM traffic 1.07x the algorithmic bytes"},
-            "fp64": {"flop_per_cell_executed": FLOP_PER_CELL, "achieved_TFLOP/s": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
-                     "peak_TFLOP/s": 33.9 * world, "frac": FLOP_PER_CELL * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (33.9 * world),
-                     "source": "executed DFMA/DMUL/DADD thread instructions from ncu (profiles/r1c_ncu_full_L_p1tet_pipe.txt); peak = tools/microbench.cu on this pool (profiles/r1_microbench_b200.txt)"},
+                         "note": "the J kernel's binding ceiling is the fp64 pipe, not HBM (SURVEY 8d, DESIGN.md 4.3): see the fp64 block"},
+            "fp64": {"flop_per_cell_executed": flop_per_cell, "achieved_TFLOP/s": flop_per_cell * nc_total / (kernel_ms_avg * 1e-3) / 1e12,
+                     "peak_TFLOP/s": fp64_peak * world, "frac": flop_per_cell * nc_total / (kernel_ms_avg * 1e-3) / 1e12 / (fp64_peak * world),
+                     "peak_source": "DFMA micro-benchmark run live in this process (nsgpu_fp64_peak)",
+                     "flop_source": (prof["source"] if prof else "instruction-count model of the row-owner algebra (DESIGN.md 4.3); no ncu capture of this kernel/workload on file")},
             "residual_only": {"ms": f_ms, "Mcells/s": nc_total / (f_ms * 1e-3) / 1e6, "GB/s": b_f / (f_ms * 1e-3) / 1e9,
                               "frac": b_f / (f_ms * 1e-3) / 1e9 / hbm_total},
             "jacobian_only": {"ms": j_ms, "Mcells/s": nc_total / (j_ms * 1e-3) / 1e6},
@@ -306,8 +328,12 @@ def run_ours(args):
                      "moved_GB/s": (8.0 * nnz_total + 8.0 * nnz_total / 16 + 56.0 * ndof_total / 4 + 16.0 * ndof_total) / (s_ms * 1e-3) / 1e9},
             "e2e": {"value": nc_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 8 * ndof_total,
                     "d2h_bytes_per_step": 8 * ndof_total, "ms_per_step": e2e_ms,
-                    "what": "NSAssembler.jacobian_residual(x_host_pinned) -> F_host; J stays device-resident for MatMult (MatShell mode)",
-                    "F_l1_checksum": f_checksum},
+                    "what": "NSAssembler.jacobian_residual(x_host_pinned) -> F_host; J stays device-resident for MatMult (MatShell mode)"},
+            "e2e_aij": {"ms_per_step": e2e_aij_ms, "Mcells/s": (nc_total / (e2e_aij_ms * 1e-3) / 1e6) if e2e_aij_ms else None,
+                        "d2h_bytes_per_step": 8 * ndof_total + 8 * nnz_total,
+                        "what": "same call with the CSR values copied to pinned host memory too (AIJ mode: PCIe-bound)"},
+            "checksums": {"F_l2": f_checksum, "J_frobenius": j_checksum,
+                          "what": "norms over all ranks' owned rows after one assembly: equal (to rounding) at every GPU count"},
             "snes_iterate": {"ms": snes_ms, "what": "NonlinearPDE_SNESProblem-style callback pair per Newton iterate: nsgpu_residual(x_host) -> F_host "
                                                       "then nsgpu_jacobian(x_host) (J stays resident), option fuse_fj: the residual pass assembles J, the Jacobian "
                                                       "call recognises the state on the device and reuses it"},
@@ -318,7 +344,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_sample_run(1, 0, n_cross, build_pattern_on_gpu=True)
+            r = cpu_sample_run(1, 1, args.workload)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     for p in (x_dev, F_dev, y_dev):
@@ -343,6 +369,7 @@ def main():
     ap.add_argument("--pipe", type=int, default=None, help="0: do not use the software-pipelined variant either (plain tile kernel)")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aij", action="store_true", help="skip the AIJ-mode end-to-end step (values to pinned host memory)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -132,6 +132,10 @@ int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_d
 int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev);
 int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out);
 
+/* Frobenius norm of the resident Jacobian over the rows owned by all ranks (MatNorm(NORM_FROBENIUS)); a partition-independent
+ * checksum of an assembly.  Collective. */
+int nsgpu_values_norm(nsgpu_ctx* ctx, double* out);
+
 /* Replace the matrix values (e.g. to use nsgpu_spmv with a matrix assembled elsewhere). */
 int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals);
 int nsgpu_get_values(nsgpu_ctx* ctx, double* vals);
@@ -170,6 +174,9 @@ const char* nsgpu_last_spmv_name(const nsgpu_ctx* ctx);
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.
  * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build. */
 int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n);
+/* Measured FP64 ceiling of ctx's GPU: DFMA TFLOP/s of a register-resident loop (8 chains/thread, 64 warps/SM), the
+ * denominator of the benchmark's fp64 fraction (SURVEY 8d asks for a measured DFMA peak). Takes ~20 ms. */
+int nsgpu_fp64_peak(nsgpu_ctx* ctx, double* tflops);
 /* Kernel launches issued by this context since creation (bench.py's "gpu_launches"). */
 int64_t nsgpu_launch_count(nsgpu_ctx* ctx);
 /* Device time (ms) of the main kernel(s) of the last *_dev call; synchronises on that call's end event. */

@@ -532,6 +532,14 @@ int64_t oracle_build_pattern(int nd, int64_t n_cells, const int32_t *dofmap, int
   return indptr[n_rows];
 }
 
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

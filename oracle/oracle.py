@@ -177,5 +177,10 @@ def spmv(indptr, indices, vals, xv):
     return y
 
 
+def set_num_threads(n):
+    """OpenMP team size of the oracle's loops (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants all cores)."""
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))
+
+
 def num_threads():
     return int(lib().oracle_num_threads())

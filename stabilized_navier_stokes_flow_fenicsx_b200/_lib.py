@@ -45,6 +45,7 @@ SIGNATURES = {
                                        ctypes.POINTER(ctypes.c_int), c_f64p, c_f64p]),
     "nsgpu_axpy_dev": (ctypes.c_int, [c_ctx, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "nsgpu_norm_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, c_f64p]),
+    "nsgpu_values_norm": (ctypes.c_int, [c_ctx, c_f64p]),
     "nsgpu_set_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),
     "nsgpu_get_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),
     "nsgpu_jacobian_residual_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "nsgpu_last_spmv_name": (ctypes.c_char_p, [c_ctx]),
     "nsgpu_set_option": (ctypes.c_int, [c_ctx, ctypes.c_char_p, ctypes.c_int64]),
     "nsgpu_timers": (ctypes.c_int, [c_ctx, c_f64p, ctypes.c_int]),
+    "nsgpu_fp64_peak": (ctypes.c_int, [c_ctx, c_f64p]),
     "nsgpu_launch_count": (ctypes.c_int64, [c_ctx]),
     "nsgpu_last_kernel_ms": (ctypes.c_int, [c_ctx, c_f64p]),
     "nsgpu_timer_start": (ctypes.c_int, [c_ctx]),

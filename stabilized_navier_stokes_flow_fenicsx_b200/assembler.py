@@ -228,6 +228,12 @@ class NSAssembler:
                 self.dev_free(F_dev); self.dev_free(dw_dev)
         return hist
 
+    def values_norm(self):
+        """Frobenius norm of the resident Jacobian over all ranks' owned rows (a partition-independent checksum)."""
+        out = ctypes.c_double()
+        self._check(self.lib.nsgpu_values_norm(self.ctx, ctypes.byref(out)), "values_norm")
+        return out.value
+
     def set_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         self._check(self.lib.nsgpu_set_values(self.ctx, _ptr(vals)), "set_values")
@@ -261,6 +267,12 @@ class NSAssembler:
 
     def last_spmv_name(self):
         return self.lib.nsgpu_last_spmv_name(self.ctx).decode()
+
+    def fp64_peak(self):
+        """Measured DFMA TFLOP/s of this GPU (live micro-benchmark)."""
+        out = ctypes.c_double()
+        self._check(self.lib.nsgpu_fp64_peak(self.ctx, ctypes.byref(out)), "fp64_peak")
+        return out.value
 
     def launch_count(self):
         return int(self.lib.nsgpu_launch_count(self.ctx))

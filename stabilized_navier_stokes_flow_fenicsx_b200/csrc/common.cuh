@@ -168,6 +168,7 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
 int k_bc_diagonal_launch(nsgpu_ctx* ctx);
 int check_finite_impl(nsgpu_ctx* ctx, const double* d_v, int64_t n, const char* what, bool sync_now);
 int spmv_impl(nsgpu_ctx* ctx, const double* d_x, double* d_y);
+int dfma_peak_impl(nsgpu_ctx* ctx, double* tflops);
 int halo_forward(nsgpu_ctx* ctx, double* d_v);
 int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);
 int rows_exchange_add(nsgpu_ctx* ctx);
@@ -178,6 +179,7 @@ int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, doub
                double* rnorm_out, double* r0norm_out);
 int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y);
 int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
+int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
 void krylov_free(nsgpu_ctx* ctx);
 // renumber.cu
 int renumber_build(nsgpu_ctx* ctx);

@@ -288,6 +288,7 @@ static int apply_op(nsgpu_ctx* ctx, Work& k, int bs, const double* y, double* ou
 }
 
 int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
+int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
 
 // KSPSolve with KSPTFQMR.  d_b: n_owned right-hand side; d_x: n_cols, initial guess in / solution out (owned part).
 int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, double atol, int max_it, int pc, bool zero_guess, int* its_out,
@@ -386,13 +387,16 @@ int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y) {
   return NSGPU_OK;
 }
 
-int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out) {
+int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out) { return norm_n_impl(ctx, d_x, ctx->n_owned, out); }
+
+// sqrt of the sum of squares of n entries, summed over all ranks
+int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out) {
   Work* kp = nullptr;
   int rc;
   if ((rc = ensure_work(ctx, &kp))) return rc;
   cudaStream_t s = ctx->stream;
-  const unsigned g = vgrid(ctx->n_owned);
-  k_dot<<<g, RED_THREADS, 0, s>>>(ctx->n_owned, d_x, d_x, kp->partial);
+  const unsigned g = vgrid(n);
+  k_dot<<<g, RED_THREADS, 0, s>>>(n, d_x, d_x, kp->partial);
   k_sum_partials<<<1, RED_THREADS, 0, s>>>((int)g, kp->partial, kp->scal);
   ctx->launches += 2;
   if (ctx->nranks > 1 && (rc = allreduce_sum(ctx, kp->scal + S_RED, 1))) return rc;

@@ -569,6 +569,14 @@ int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out) {
   return norm_impl(ctx, x_dev, out);
 }
 
+int nsgpu_values_norm(nsgpu_ctx* ctx, double* out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built && out, "values_norm: no pattern or NULL output");
+  int64_t nnz_owned = 0;
+  NS_CUDA(ctx, cudaMemcpy(&nnz_owned, ctx->d_indptr + ctx->n_owned, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return norm_n_impl(ctx, ctx->d_vals, nnz_owned, out);
+}
+
 int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
   if (ctx) ctx->jac_valid = false;   // whatever changes, the resident Jacobian no longer belongs to a remembered state
   NS_ENTER(ctx);
@@ -710,6 +718,12 @@ int nsgpu_last_kernel_ms(nsgpu_ctx* ctx, double* ms) {
   NS_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
   *ms = t;
   return NSGPU_OK;
+}
+
+int nsgpu_fp64_peak(nsgpu_ctx* ctx, double* tflops) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, tflops != nullptr, "NULL output");
+  return dfma_peak_impl(ctx, tflops);
 }
 
 int64_t nsgpu_launch_count(nsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
