@@ -131,6 +131,8 @@ int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_d
  * the owned entries; the norm is reduced over all ranks): y += a x, *out = ||x||_2. */
 int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev);
 int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out);
+/* VecDot over the owned entries, reduced over all ranks (the initial slope F . J dx of SNES' backtracking line search). */
+int nsgpu_dot_dev(nsgpu_ctx* ctx, const double* x_dev, const double* y_dev, double* out);
 
 /* Frobenius norm of the resident Jacobian over the rows owned by all ranks (MatNorm(NORM_FROBENIUS)); a partition-independent
  * checksum of an assembly.  Collective. */

@@ -45,6 +45,7 @@ SIGNATURES = {
                                        ctypes.POINTER(ctypes.c_int), c_f64p, c_f64p]),
     "nsgpu_axpy_dev": (ctypes.c_int, [c_ctx, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "nsgpu_norm_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, c_f64p]),
+    "nsgpu_dot_dev": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_void_p, c_f64p]),
     "nsgpu_values_norm": (ctypes.c_int, [c_ctx, c_f64p]),
     "nsgpu_set_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),
     "nsgpu_get_values": (ctypes.c_int, [c_ctx, ctypes.c_void_p]),

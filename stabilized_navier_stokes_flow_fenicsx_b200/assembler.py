@@ -152,33 +152,52 @@ class NSAssembler:
         return n.value
 
     # ------------------------------------------------------------------ the hot path
+    def _state(self, x):
+        """The C ABI reads n_owned + n_ghost values from x_local (it cannot see lengths): check here.  A vector that only
+        holds the owned entries (a petsc4py ``Vec.array``) is padded -- the ghost part is refreshed by the forward halo inside."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        if x.size >= self.n_dofs:
+            return x
+        if x.size == self.n_owned:
+            xg = np.zeros(self.n_dofs)
+            xg[: self.n_owned] = x
+            return xg
+        raise ValueError(f"state vector has {x.size} entries; expected n_owned = {self.n_owned} or n_owned + n_ghost = {self.n_dofs}")
+
+    def _out(self, out, n, what):
+        if out is None:
+            return np.empty(n)
+        if not isinstance(out, np.ndarray) or out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n:
+            raise ValueError(f"{what}: need a C-contiguous float64 array with at least {n} entries")
+        return out
+
     def residual(self, x, out=None):
         """F of NavierStokesChannelFlow.py:51-67 (assemble_vector + apply_lifting + reverse halo + set_bc)."""
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        out = np.empty(self.n_dofs) if out is None else out
+        x = self._state(x)
+        out = self._out(out, self.n_dofs, "residual output")
         self._check(self.lib.nsgpu_residual(self.ctx, _ptr(x), _ptr(out)), "residual")
         return out
 
     def jacobian(self, x, out=None, fetch=True):
         """J of NavierStokesChannelFlow.py:69-75.  fetch=False keeps the values on the device (MatShell)."""
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        if fetch and out is None:
-            out = np.empty(self.nnz)
+        x = self._state(x)
+        if fetch:
+            out = self._out(out, self.nnz, "Jacobian values")
         self._check(self.lib.nsgpu_jacobian(self.ctx, _ptr(x), _ptr(out) if fetch else None), "jacobian")
         return out
 
     def jacobian_residual(self, x, vals_out=None, F_out=None, fetch_vals=True):
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        F_out = np.empty(self.n_dofs) if F_out is None else F_out
-        if fetch_vals and vals_out is None:
-            vals_out = np.empty(self.nnz)
+        x = self._state(x)
+        F_out = self._out(F_out, self.n_dofs, "residual output")
+        if fetch_vals:
+            vals_out = self._out(vals_out, self.nnz, "Jacobian values")
         self._check(self.lib.nsgpu_jacobian_residual(self.ctx, _ptr(x), _ptr(vals_out) if fetch_vals else None, _ptr(F_out)), "jacobian_residual")
         return vals_out, F_out
 
     def mult(self, x, out=None):
         """PETSc MatMult with the last assembled Jacobian: y_owned = J x."""
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        out = np.empty(self.n_owned) if out is None else out
+        x = self._state(x)
+        out = self._out(out, self.n_owned, "MatMult output")
         self._check(self.lib.nsgpu_spmv(self.ctx, _ptr(x), _ptr(out)), "spmv")
         return out
 
@@ -206,26 +225,77 @@ class NSAssembler:
         self._check(self.lib.nsgpu_norm_dev(self.ctx, x_dev, ctypes.byref(out)), "norm_dev")
         return out.value
 
-    def newton_dev(self, w_dev, rtol=1e-8, atol=1e-8, max_it=30, ksp_rtol=1e-8, ksp_max_it=2000, pc=4, work=None):
+    def dot_dev(self, x_dev, y_dev):
+        out = ctypes.c_double()
+        self._check(self.lib.nsgpu_dot_dev(self.ctx, x_dev, y_dev, ctypes.byref(out)), "dot_dev")
+        return out.value
+
+    def newton_dev(self, w_dev, rtol=1e-8, atol=1e-8, max_it=30, ksp_rtol=1e-8, ksp_max_it=2000, pc=4, work=None, linesearch="bt"):
         """Device-resident Newton iteration with the SNES settings of the reference (snes_rtol / snes_atol 1e-8, max_it 30,
-        NavierStokesChannelFlow.py:286-291; basic line search): F and J from the assembly kernels, dw from TFQMR, w -= dw.
-        Nothing but a few scalars crosses PCIe.  w_dev: n_cols doubles (state in / solution out).  Returns the history."""
+        NavierStokesChannelFlow.py:286-291): F and J from the assembly kernels, dw from TFQMR, w -= lambda dw.
+        ``linesearch``: "bt" = PETSc's default for newtonls (SNESLineSearchBT: sufficient decrease alpha = 1e-4 on
+        1/2 ||F||^2, quadratic then cubic backtracking, steps clipped to [0.1, 0.5] of the previous one, at most 40), or
+        "basic" (full steps).  Nothing but a few scalars crosses PCIe.  w_dev: n_cols doubles (state in / solution out)."""
         nbytes = 8 * self.n_cols
-        F_dev, dw_dev = work if work is not None else (self.dev_alloc(nbytes), self.dev_alloc(nbytes))
+        owns = work is None
+        F_dev, dw_dev = (self.dev_alloc(nbytes), self.dev_alloc(nbytes)) if owns else work[:2]
+        Jd_dev = None
         hist = []
         try:
+            self.jacobian_residual_dev(w_dev, True, F_dev)
+            fn = self.norm_dev(F_dev)
             for it in range(max_it + 1):
-                self.jacobian_residual_dev(w_dev, True, F_dev)
-                fn = self.norm_dev(F_dev)
                 hist.append({"it": it, "fnorm": fn})
                 if fn <= atol or (it > 0 and fn <= rtol * hist[0]["fnorm"]) or it == max_it:
                     break
                 info = self.tfqmr_dev(F_dev, dw_dev, rtol=ksp_rtol, max_it=ksp_max_it, pc=pc)
                 hist[-1].update(ksp_its=info["its"], ksp_rnorm=info["rnorm"])
-                self.axpy_dev(-1.0, dw_dev, w_dev)
+                if linesearch == "basic":
+                    self.axpy_dev(-1.0, dw_dev, w_dev)
+                    self.jacobian_residual_dev(w_dev, True, F_dev)
+                    fn = self.norm_dev(F_dev)
+                    continue
+                # initial slope of phi(lambda) = 1/2 ||F(w - lambda dw)||^2 at 0:  -F . (J dw)   (PETSc: MatMult + VecDot)
+                if Jd_dev is None:
+                    Jd_dev = self.dev_alloc(nbytes)
+                self.spmv_dev(dw_dev, Jd_dev)
+                slope = -self.dot_dev(F_dev, Jd_dev)
+                if slope > 0.0:
+                    slope = -slope
+                if slope == 0.0:
+                    slope = -1.0
+                f0 = 0.5 * fn * fn
+                lam, lam_prev, g_prev, steps = 1.0, None, None, 0
+                self.axpy_dev(-lam, dw_dev, w_dev)
+                while True:
+                    self.jacobian_residual_dev(w_dev, True, F_dev)
+                    gn = self.norm_dev(F_dev)
+                    g = 0.5 * gn * gn
+                    if (np.isfinite(g) and g <= f0 + 1e-4 * lam * slope) or steps >= 40:
+                        break
+                    if lam_prev is None or not np.isfinite(g):                     # quadratic fit through phi(0), phi'(0), phi(lam)
+                        lam_new = -slope * lam * lam / (2.0 * (g - f0 - lam * slope)) if np.isfinite(g) else 0.5 * lam
+                    else:                                                          # cubic through the last two trial points
+                        t1, t2 = g - f0 - lam * slope, g_prev - f0 - lam_prev * slope
+                        ca = (t1 / lam ** 2 - t2 / lam_prev ** 2) / (lam - lam_prev)
+                        cb = (-lam_prev * t1 / lam ** 2 + lam * t2 / lam_prev ** 2) / (lam - lam_prev)
+                        if ca == 0.0:
+                            lam_new = -slope / (2.0 * cb)
+                        else:
+                            disc = cb * cb - 3.0 * ca * slope
+                            lam_new = 0.5 * lam if disc < 0.0 else ((-cb + np.sqrt(disc)) / (3.0 * ca) if cb <= 0.0 else -slope / (cb + np.sqrt(disc)))
+                    lam_new = min(max(lam_new, 0.1 * lam), 0.5 * lam)
+                    lam_prev, g_prev = lam, g
+                    self.axpy_dev(lam - lam_new, dw_dev, w_dev)                    # w = w0 - lam_new dw
+                    lam = lam_new
+                    steps += 1
+                hist[-1].update(lam=lam, ls_steps=steps)
+                fn = gn
         finally:
-            if work is None:
+            if owns:
                 self.dev_free(F_dev); self.dev_free(dw_dev)
+            if Jd_dev is not None:
+                self.dev_free(Jd_dev)
         return hist
 
     def values_norm(self):
@@ -329,20 +399,58 @@ class NSAssembler:
 
 
 def _as_array(v):
-    """NumPy view of a NumPy array or of a petsc4py Vec (``.array``)."""
-    return v if isinstance(v, np.ndarray) else v.array
+    """NumPy view of a NumPy array or of a petsc4py Vec.  A ghosted Vec is opened through its local form (owned + ghost
+    entries, what dolfinx's ``x.localForm()`` gives, NavierStokesChannelFlow.py:57-60); a plain Vec through ``.array``."""
+    if isinstance(v, np.ndarray):
+        return v
+    gl = getattr(v, "getLocalForm", None) or getattr(v, "localForm", None)
+    if gl is not None:
+        try:
+            loc = gl()
+            arr = getattr(loc, "array", None)
+            if arr is None and hasattr(loc, "__enter__"):
+                arr = loc.__enter__().array
+            if arr is not None:
+                return arr
+        except Exception:
+            pass
+    return v.array
+
+
+def _fill_matrix(J, asm, pattern, vals, local_to_global=None):
+    """Hand the owned rows of the CSR triple to a petsc4py-like Mat.  Column indices of the pattern are LOCAL (owned, then
+    ghosts, then column ghosts): ``setValuesLocalCSR`` takes them as they are (dolfinx's create_matrix installs the
+    local-to-global maps); ``setValuesCSR`` wants global columns, so a map is required as soon as ghosts exist."""
+    indptr, indices = pattern
+    n = asm.n_owned
+    if int(indptr[n]) > np.iinfo(np.int32).max:
+        raise OverflowError(f"{int(indptr[n])} entries in the owned rows do not fit PETSc's 32-bit PetscInt row pointers; "
+                            "use more ranks or the MatShell mode (values stay on the device)")
+    ip = indptr[: n + 1].astype(np.int32)
+    ix, v = indices[: indptr[n]], vals[: indptr[n]]
+    J.zeroEntries()
+    if hasattr(J, "setValuesLocalCSR") and local_to_global is None:
+        J.setValuesLocalCSR(ip, ix, v)
+    else:
+        if local_to_global is not None:
+            ix = np.asarray(local_to_global)[ix].astype(np.int32)
+        elif getattr(asm, "n_cols", asm.n_dofs) > asm.n_owned:
+            raise ValueError("Mat.setValuesCSR needs global column indices: pass local_to_global (owned + ghost + column ghosts)")
+        J.setValuesCSR(ip, ix, v)
+    J.assemble()
 
 
 class NonlinearPDE_SNESProblem:
     """Same role and callback signatures as the class of that name in
     NavierStokes/NavierStokesChannelFlow.py:40-75.  ``F``/``J`` accept NumPy arrays or petsc4py objects:
-    a Vec is accessed through ``.array``; a Mat is filled with ``setValuesCSR`` when it has that method,
-    otherwise ``J`` is treated as the CSR value array itself."""
+    a Vec is accessed through its ghosted local form (or ``.array``); a Mat is filled with ``setValuesLocalCSR`` /
+    ``setValuesCSR``, otherwise ``J`` is treated as the CSR value array itself."""
 
-    def __init__(self, assembler, u=None, fuse=True):
+    def __init__(self, assembler, u=None, fuse=True, local_to_global=None):
         self.asm = assembler
         self.u = u                       # optional mirror of the state vector (self.u of the reference)
         self.pattern = None
+        self.local_to_global = local_to_global
         # SNES evaluates F and then J at the same iterate: with fuse the residual call assembles the Jacobian in the same
         # pass (it stays on the device) and the Jacobian call that follows recognises the state and reuses it.
         self.asm.set_option("fuse_fj", 1 if fuse else 0)
@@ -355,22 +463,81 @@ class NonlinearPDE_SNESProblem:
         """Assemble residual vector (x.ghostUpdate, assemble_vector, apply_lifting, F.ghostUpdate, set_bc)."""
         xa = _as_array(x)
         if self.u is not None:
-            _as_array(self.u)[:] = xa     # x.copy(self.u.x.petsc_vec)
+            ua = _as_array(self.u)
+            ua[: xa.size] = xa[: ua.size]     # x.copy(self.u.x.petsc_vec)
         Fa = _as_array(F)
         res = self.asm.residual(xa)
         Fa[: self.asm.n_owned] = res[: self.asm.n_owned]
-        if Fa.size == self.asm.n_dofs:
+        if Fa.size > self.asm.n_owned:
             Fa[self.asm.n_owned:] = 0.0   # ghost part of F is zero after the reverse scatter
 
     def J(self, snes, x, J, P=None):
         """Assemble Jacobian matrix (zeroEntries, assemble_matrix with bcs, assemble)."""
         xa = _as_array(x)
         vals = self.asm.jacobian(xa)
-        if hasattr(J, "setValuesCSR"):
-            indptr, indices = self.pattern if self.pattern is not None else self.create_matrix()
-            n = self.asm.n_owned
-            J.zeroEntries()
-            J.setValuesCSR(indptr[: n + 1].astype(np.int32), indices[: indptr[n]], vals[: indptr[n]])
-            J.assemble()
+        if hasattr(J, "setValuesCSR") or hasattr(J, "setValuesLocalCSR"):
+            _fill_matrix(J, self.asm, self.pattern if self.pattern is not None else self.create_matrix(), vals, self.local_to_global)
         else:
             _as_array(J)[:] = vals
+
+
+class NonlinearProblem:
+    """The three callbacks dolfinx.nls.petsc.NewtonSolver takes from dolfinx.fem.petsc.NonlinearProblem
+    (LidDrivenFlow/LidDrivenNavierStokesFlow.py:150-153): ``form(x)`` (ghost update before an assembly), ``F(x, b)``
+    (assemble_vector + apply_lifting(x0 = x, alpha = -1) + ghost reverse-add + set_bc(x0 = x, alpha = -1)) and ``J(x, A)``
+    (zeroEntries + assemble_matrix(bcs) + assemble).  ``x`` / ``b``: NumPy arrays or petsc4py Vecs; ``A``: a petsc4py-like
+    Mat or the CSR value array.  ``solver.setF(problem.F, b); solver.setJ(problem.J, A); solver.set_form(problem.form)``."""
+
+    def __init__(self, assembler, u=None, local_to_global=None):
+        self.asm = assembler
+        self.u = u
+        self.local_to_global = local_to_global
+        self.pattern = None
+        self.asm.set_option("fuse_fj", 1)      # NewtonSolver calls F then J at the same iterate
+
+    def create_matrix(self):
+        self.pattern = self.asm.create_matrix()
+        return self.pattern
+
+    def form(self, x):
+        """x.ghostUpdate(INSERT, FORWARD): the library refreshes the ghost entries itself inside F / J (halo over NCCL), so
+        there is nothing to do beyond keeping the state mirror in step."""
+        if self.u is not None:
+            xa, ua = _as_array(x), _as_array(self.u)
+            ua[: xa.size] = xa[: ua.size]
+
+    def F(self, x, b):
+        ba = _as_array(b)
+        res = self.asm.residual(_as_array(x))
+        ba[: self.asm.n_owned] = res[: self.asm.n_owned]
+        if ba.size > self.asm.n_owned:
+            ba[self.asm.n_owned:] = 0.0
+
+    def J(self, x, A):
+        vals = self.asm.jacobian(_as_array(x))
+        if hasattr(A, "setValuesCSR") or hasattr(A, "setValuesLocalCSR"):
+            _fill_matrix(A, self.asm, self.pattern if self.pattern is not None else self.create_matrix(), vals, self.local_to_global)
+        else:
+            _as_array(A)[:] = vals
+
+
+def newton_solve(problem, x, linear_solve, rtol=1e-9, atol=1e-10, max_it=50, relaxation=1.0, criterion="incremental", A=None, b=None):
+    """The iteration dolfinx's NewtonSolver runs on a NonlinearProblem (LidDrivenNavierStokesFlow.py:152-169):
+    form, F, J, solve J dx = F, x -= relaxation dx, until the incremental (||dx|| < rtol ||dx_0|| or < atol) or residual
+    criterion holds.  ``linear_solve(A_values, b_owned) -> dx_owned`` stands for the KSP (preonly + LU in the lid-driven
+    script).  x: NumPy array (owned + ghost); returns (iterations, converged)."""
+    asm = problem.asm
+    b = np.zeros(asm.n_dofs) if b is None else b
+    A = np.zeros(asm.nnz) if A is None else A
+    r0 = None
+    for it in range(1, max_it + 1):
+        problem.form(x)
+        problem.F(x, b)
+        problem.J(x, A)
+        dx = linear_solve(A, b[: asm.n_owned])
+        x[: asm.n_owned] -= relaxation * dx
+        r = float(np.linalg.norm(dx)) if criterion == "incremental" else float(np.linalg.norm(b[: asm.n_owned]))
+        r0 = r if r0 is None else r0
+        if r < atol or (r0 > 0 and r / r0 < rtol):
+            return it, True
+    return max_it, False

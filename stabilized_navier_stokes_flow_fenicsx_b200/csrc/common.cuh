@@ -180,6 +180,7 @@ int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, doub
 int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y);
 int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
 int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
+int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out);
 void krylov_free(nsgpu_ctx* ctx);
 // renumber.cu
 int renumber_build(nsgpu_ctx* ctx);

@@ -389,6 +389,22 @@ int axpy_impl(nsgpu_ctx* ctx, double a, const double* d_x, double* d_y) {
 
 int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out) { return norm_n_impl(ctx, d_x, ctx->n_owned, out); }
 
+// VecDot over the owned entries, summed over all ranks
+int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out) {
+  Work* kp = nullptr;
+  int rc;
+  if ((rc = ensure_work(ctx, &kp))) return rc;
+  cudaStream_t s = ctx->stream;
+  const unsigned g = vgrid(ctx->n_owned);
+  k_dot<<<g, RED_THREADS, 0, s>>>(ctx->n_owned, d_x, d_y, kp->partial);
+  k_sum_partials<<<1, RED_THREADS, 0, s>>>((int)g, kp->partial, kp->scal);
+  ctx->launches += 2;
+  if (ctx->nranks > 1 && (rc = allreduce_sum(ctx, kp->scal + S_RED, 1))) return rc;
+  NS_CUDA(ctx, cudaMemcpyAsync(out, kp->scal + S_RED, sizeof(double), cudaMemcpyDeviceToHost, s));
+  NS_CUDA(ctx, cudaStreamSynchronize(s));
+  return NSGPU_OK;
+}
+
 // sqrt of the sum of squares of n entries, summed over all ranks
 int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out) {
   Work* kp = nullptr;

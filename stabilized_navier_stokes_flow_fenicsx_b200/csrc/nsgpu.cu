@@ -563,6 +563,12 @@ int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev)
   return axpy_impl(ctx, a, x_dev, y_dev);
 }
 
+int nsgpu_dot_dev(nsgpu_ctx* ctx, const double* x_dev, const double* y_dev, double* out) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, x_dev && y_dev && out, "dot: NULL argument");
+  return dot_impl(ctx, x_dev, y_dev, out);
+}
+
 int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out) {
   NS_ENTER(ctx);
   NS_REQUIRE(ctx, x_dev && out, "norm: NULL argument");

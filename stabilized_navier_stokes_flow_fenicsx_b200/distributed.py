@@ -43,6 +43,13 @@ class Comm:
             dist.init_process_group(backend=backend, rank=rank, world_size=size)
         return Comm(rank, size, dist, device)
 
+    @staticmethod
+    def from_mpi4py(comm, local_rank=None):
+        """The communicator a dolfinx script already has (``mesh.comm`` / ``MPI.COMM_WORLD``,
+        NavierStokes/NavierStokesChannelFlow.py:99-101, launched by ``mpirun -n 6``): same facade as the torchrun one, over
+        mpi4py.  The NCCL unique id of the library's own communicator travels through ``bcast_bytes``."""
+        return MpiComm(comm, local_rank)
+
     def _t(self, arr):
         import torch
         t = torch.from_numpy(np.ascontiguousarray(arr))
@@ -111,6 +118,37 @@ class Comm:
         if self.size > 1 and self.dist.is_initialized():
             self.dist.barrier()
             self.dist.destroy_process_group()
+
+
+class MpiComm(Comm):
+    """Comm facade over an mpi4py communicator (anything with Get_rank / Get_size / Barrier / allreduce / bcast / alltoall)."""
+
+    def __init__(self, comm, local_rank=None):
+        super().__init__(comm.Get_rank(), comm.Get_size(), None, None)
+        self.comm = comm
+        self.local_rank = self.rank if local_rank is None else local_rank
+
+    def barrier(self):
+        if self.size > 1:
+            self.comm.Barrier()
+
+    def max(self, v):
+        return v if self.size == 1 else max(self.comm.allgather(float(v)))
+
+    def sum(self, v):
+        return v if self.size == 1 else int(sum(self.comm.allgather(int(v))))
+
+    def bcast_bytes(self, data, n, root=0):
+        return data if self.size == 1 else self.comm.bcast(data if self.rank == root else None, root=root)
+
+    def exchange(self, send):
+        if self.size == 1:
+            return {}
+        out = self.comm.alltoall([np.asarray(send[p], dtype=np.int64) if p in send else None for p in range(self.size)])
+        return {p: np.asarray(a, dtype=np.int64) for p, a in enumerate(out) if a is not None and p != self.rank and len(a)}
+
+    def close(self):
+        self.barrier()
 
 
 # ------------------------------------------------------------------------------------------------ partition

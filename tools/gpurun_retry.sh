@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <timeout> <command...>   -- retries while the pod answers "transient" / busy (nothing is charged for those)
+T=$1; shift
+for i in $(seq 1 40); do
+  out=$(/usr/local/graft/bin/gpurun --timeout "$T" -- "$@" 2>&1); rc=$?
+  if echo "$out" | grep -q "status=transient\|status=busy" || [ $rc -eq 3 ]; then sleep 90; continue; fi
+  echo "$out" | tail -40; exit $rc
+done
+echo "gave up after 40 tries"; exit 3
