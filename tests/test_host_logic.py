@@ -6,7 +6,10 @@ import os
 
 import numpy as np
 
-from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NonlinearPDE_SNESProblem
+import pytest
+
+from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler, NonlinearPDE_SNESProblem, NonlinearProblem, newton_solve
+from stabilized_navier_stokes_flow_fenicsx_b200.distributed import Comm
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -56,12 +59,94 @@ def test_snes_jacobian_into_a_petsc_like_matrix():
         def setValuesCSR(self, ip, ix, v): self.csr = (np.array(ip), np.array(ix), np.array(v))
         def assemble(self): self.assembled = True
     asm = _FakeAssembler(n_owned=4, n_ghost=1, nnz=5)
-    prob = NonlinearPDE_SNESProblem(asm)
+    with pytest.raises(ValueError, match="global column"):      # local column indices must not reach setValuesCSR once ghosts exist
+        NonlinearPDE_SNESProblem(asm).J(None, np.zeros(asm.n_dofs), Mat(), None)
+    prob = NonlinearPDE_SNESProblem(asm, local_to_global=100 + np.arange(asm.n_dofs))
     A = Mat()
     prob.J(None, np.zeros(asm.n_dofs), A, None)
     ip, ix, v = A.csr
     assert A.zeroed and A.assembled and ip.dtype == np.int32    # PetscInt of the pinned build is 32-bit
     assert len(ip) == asm.n_owned + 1 and len(ix) == ip[-1] == len(v)   # owned rows only: ghost rows were shipped to their owners
+    np.testing.assert_array_equal(ix, 100 + np.arange(len(ix)))          # global columns
+
+    class LocalMat(Mat):                                         # dolfinx's create_matrix installs local-to-global maps
+        def setValuesLocalCSR(self, ip, ix, v): self.local = (np.array(ip), np.array(ix), np.array(v))
+    B = LocalMat()
+    NonlinearPDE_SNESProblem(asm).J(None, np.zeros(asm.n_dofs), B, None)
+    np.testing.assert_array_equal(B.local[1], np.arange(len(B.local[1])))
+
+
+def test_row_pointers_beyond_int32_are_refused():
+    class Mat:
+        def zeroEntries(self): pass
+        def setValuesLocalCSR(self, ip, ix, v): raise AssertionError("must not be reached")
+        def assemble(self): pass
+    class Big(_FakeAssembler):
+        def create_matrix(self):
+            return np.array([0, 2 ** 31 + 5, 2 ** 31 + 6], dtype=np.int64), np.zeros(1, dtype=np.int32)
+    asm = Big(n_owned=1, n_ghost=1, nnz=1)
+    with pytest.raises(OverflowError, match="32-bit"):
+        NonlinearPDE_SNESProblem(asm).J(None, np.zeros(2), Mat(), None)
+
+
+def test_nonlinear_problem_adapter_and_newton_iteration():
+    """dolfinx NonlinearProblem shape (LidDrivenNavierStokesFlow.py:150-169): form(x), F(x, b), J(x, A) driving the
+    incremental-criterion Newton iteration.  The stand-in problem is F(x) = x^2 - c (J diagonal)."""
+    class Quad(_FakeAssembler):
+        def __init__(self):
+            super().__init__(n_owned=5, n_ghost=0, nnz=5)
+            self.c = np.array([1.0, 4.0, 9.0, 16.0, 25.0])
+        def create_matrix(self):
+            return np.arange(6, dtype=np.int64), np.arange(5, dtype=np.int32)
+        def residual(self, x):
+            self.calls.append("F"); return np.asarray(x) ** 2 - self.c
+        def jacobian(self, x):
+            self.calls.append("J"); return 2.0 * np.asarray(x)
+    asm = Quad()
+    u = np.zeros(5)
+    prob = NonlinearProblem(asm, u=u)
+    assert asm.options.get("fuse_fj") == 1
+    x = np.full(5, 3.0)
+    its, ok = newton_solve(prob, x, lambda A, b: b / A, rtol=1e-12)
+    assert ok and its < 12
+    np.testing.assert_allclose(x, [1.0, 2.0, 3.0, 4.0, 5.0], rtol=1e-12)
+    assert asm.calls[:4] == ["F", "J", "F", "J"]               # F then J at every iterate
+    assert np.abs(u - x).max() < 1e-3                           # form() keeps the state mirror in step (one iterate behind at most)
+
+
+def test_state_vector_lengths_are_checked_before_the_c_abi_sees_them():
+    """the C ABI reads n_owned + n_ghost doubles from x_local; a short array must never reach it."""
+    asm = NSAssembler.__new__(NSAssembler)                       # no GPU: only the host-side checks are exercised
+    asm.n_owned, asm.n_ghost, asm.n_dofs = 6, 2, 8
+    np.testing.assert_array_equal(asm._state(np.arange(8.0)), np.arange(8.0))
+    padded = asm._state(np.arange(6.0))                          # Vec.array: owned entries only -> padded, ghosts come from the halo
+    assert padded.size == 8 and np.all(padded[6:] == 0.0)
+    with pytest.raises(ValueError, match="expected n_owned"):
+        asm._state(np.arange(5.0))
+    with pytest.raises(ValueError, match="at least 8"):
+        asm._out(np.zeros(7), 8, "residual output")
+    asm.ctx = None
+
+
+def test_comm_over_an_mpi4py_like_communicator():
+    class FakeMPI:                                               # the five calls the facade makes, single rank
+        def Get_rank(self): return 0
+        def Get_size(self): return 1
+        def Barrier(self): pass
+    c = Comm.from_mpi4py(FakeMPI())
+    assert (c.rank, c.size) == (0, 1) and c.max(3.5) == 3.5 and c.sum(7) == 7
+    assert c.bcast_bytes(b"abc", 3) == b"abc" and c.exchange({}) == {}
+    c.barrier(); c.close()
+
+    class FakeMPI2(FakeMPI):                                     # rank 0 of 2 with canned answers: checks the call shapes
+        def Get_size(self): return 2
+        def allgather(self, v): return [v, 2 * v]
+        def bcast(self, data, root=0): return data
+        def alltoall(self, lst): return [None, np.array([5, 6], dtype=np.int64)]
+    c2 = Comm.from_mpi4py(FakeMPI2())
+    assert c2.max(2.0) == 4.0 and c2.sum(3) == 9
+    out = c2.exchange({1: np.array([1, 2, 3])})
+    assert list(out) == [1] and list(out[1]) == [5, 6]
 
 
 def test_tools_parse_without_their_optional_dependencies():
