@@ -195,3 +195,65 @@ def cavity_state(space, seed=1234, noise=1e-3):
     w = np.where(c == 0, np.sin(np.pi * x) ** 2 * np.sin(2 * np.pi * y) * y,
         np.where(c == 1, -np.sin(2 * np.pi * x) * np.sin(np.pi * y) ** 2 * 0.5, 0.1 * np.cos(np.pi * x) * y))
     return w + noise * np.random.default_rng(seed).standard_normal(space.n_dofs)
+
+
+# ----------------------------------------------------------------------------------------- DFG 2D-1 (Schaefer-Turek) domain
+def dfg_cylinder_mesh(h_far=0.02, n_cyl=96, growth=1.18):
+    """Triangulation of the DFG 2D-1 benchmark domain of NavierStokes/Validation_Flow (dfg_pillar_2D.geo: channel
+    [0, 2.2] x [0, 0.41], cylinder of radius 0.05 at (0.2, 0.2)) without gmsh: points on the cylinder, on concentric rings
+    that grow geometrically away from it, and on a regular background lattice, triangulated with scipy's Delaunay; the
+    triangles inside the cylinder are dropped.  Cells are counter-clockwise."""
+    from scipy.spatial import Delaunay
+    L, H, cx, cy, r = 2.2, 0.41, 0.2, 0.2, 0.05
+    pts = []
+    th = 2 * np.pi * np.arange(n_cyl) / n_cyl
+    pts.append(np.stack([cx + r * np.cos(th), cy + r * np.sin(th)], 1))
+    ring_r, dr, k = r, 2 * np.pi * r / n_cyl, 0
+    while True:
+        dr = min(dr * growth, h_far)
+        ring_r += dr
+        if ring_r + 0.6 * h_far > min(cx, cy, H - cy):
+            break
+        k += 1
+        n = max(12, int(round(2 * np.pi * ring_r / dr)))
+        t = 2 * np.pi * (np.arange(n) + 0.5 * (k % 2)) / n
+        pts.append(np.stack([cx + ring_r * np.cos(t), cy + ring_r * np.sin(t)], 1))
+    r_out = ring_r - dr
+    nx, ny = int(round(L / h_far)), int(round(H / h_far))
+    gx, gy = np.meshgrid(np.linspace(0, L, nx + 1), np.linspace(0, H, ny + 1), indexing="ij")
+    gx = gx.copy()
+    gx[:, 1::2][1:-1] += 0.5 * L / nx                                    # staggered rows: near-equilateral triangles
+    g = np.stack([gx.ravel(), gy.ravel()], 1)
+    g = g[(g[:, 0] <= L + 1e-12)]
+    keep = np.hypot(g[:, 0] - cx, g[:, 1] - cy) > r_out + 0.7 * h_far
+    pts.append(g[keep])
+    P = np.concatenate(pts)
+    tri = Delaunay(P)
+    T = tri.simplices
+    cen = P[T].mean(axis=1)
+    inside = (np.hypot(cen[:, 0] - cx, cen[:, 1] - cy) < r * np.cos(np.pi / n_cyl)) | (T < n_cyl).all(axis=1)   # the first n_cyl points are the cylinder
+    T = T[~inside]
+    a, b, c = P[T[:, 0]], P[T[:, 1]], P[T[:, 2]]
+    area = 0.5 * ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+    T = T[np.abs(area) > 1e-14]
+    area = area[np.abs(area) > 1e-14]
+    T[area < 0] = T[area < 0][:, [0, 2, 1]]
+    used = np.unique(T)
+    remap = -np.ones(len(P), dtype=np.int64); remap[used] = np.arange(len(used))
+    x = np.zeros((len(used), 3)); x[:, :2] = P[used]
+    return Mesh(2, x, remap[T].astype(np.int32), (), {"kind": "dfg2d", "L": L, "H": H, "cx": cx, "cy": cy, "r": r, "n_cyl": n_cyl})
+
+
+def dfg_bcs(space, tol=1e-9):
+    """bc = [bcu_inflow, bcu_walls, bcu_obstacle] of DFG_2D_Validation.py:64-97: parabolic inflow 4 * 0.3 * y (0.41 - y) / 0.41^2,
+    no-slip walls and cylinder, do-nothing outflow.  Also returns the velocity dofs on the cylinder (for drag / lift)."""
+    X, c = space.dof_x, space.dof_comp
+    mt = space.mesh.meta
+    vel = c < 2
+    inflow = np.nonzero(vel & (np.abs(X[:, 0]) < tol))[0]
+    g_in = np.where(c[inflow] == 0, 4.0 * 0.3 * X[inflow, 1] * (mt["H"] - X[inflow, 1]) / mt["H"] ** 2, 0.0)
+    walls = np.nonzero(vel & ((np.abs(X[:, 1]) < tol) | (np.abs(X[:, 1] - mt["H"]) < tol)))[0]
+    on_cyl = np.abs(np.hypot(X[:, 0] - mt["cx"], X[:, 1] - mt["cy"]) - mt["r"]) < 1e-6
+    obstacle = np.nonzero(vel & on_cyl)[0]
+    bcs = [(inflow.astype(np.int32), g_in), (walls.astype(np.int32), np.zeros(len(walls))), (obstacle.astype(np.int32), np.zeros(len(obstacle)))]
+    return bcs, obstacle

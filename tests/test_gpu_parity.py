@@ -173,8 +173,11 @@ def test_arbitrary_dof_numbering(oracle, order):
     assert np.abs(asm.mult(xv) - 2.0 * yo).max() <= RTOL * 2 * np.abs(yo).max()
     asm.set_values(gv)
     b = oracle.spmv(indptr, indices, vals, xv)
+    np.testing.assert_array_equal(asm.get_values(), gv)
     xs, info = asm.tfqmr(b, rtol=1e-12, max_it=2000)
-    assert np.linalg.norm(oracle.spmv(indptr, indices, vals, xs) - b) <= 1e-9 * np.linalg.norm(b)
+    res = oracle.spmv(indptr, indices, vals, xs) - b
+    bad = np.flatnonzero(np.abs(res) > 1e-6)
+    assert np.linalg.norm(res) <= 1e-9 * np.linalg.norm(b), (info, len(bad), bad[:8], marker[bad[:8]], mult[bad[:8]], (xs / xv)[bad[:8]])
     asm.close()
 
 
