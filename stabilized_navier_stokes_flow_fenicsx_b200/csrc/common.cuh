@@ -162,6 +162,14 @@ template <typename T> int dev_alloc(nsgpu_ctx* ctx, T** p, int64_t n) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Host -> device copy ordered on the context's stream and complete on return.  (A blocking cudaMemcpy runs on the legacy
+// default stream: from pageable memory it may return before the DMA has landed, and the context's stream is non-blocking,
+// so a kernel launched right after it would not wait for it.)
+inline cudaError_t h2d_sync(nsgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  return e == cudaSuccess ? cudaStreamSynchronize(ctx->stream) : e;
+}
+
 // implemented in pattern.cu / assemble.cu / spmv.cu / halo.cu
 int build_pattern_impl(nsgpu_ctx* ctx);
 int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);

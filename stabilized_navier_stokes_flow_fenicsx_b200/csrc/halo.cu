@@ -220,8 +220,8 @@ extern "C" int nsgpu_set_halo(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_
     for (auto& d : si) if (d < ctx->n_dofs) d = ctx->h_perm[d];
     for (auto& d : ri) if (d < ctx->n_dofs) d = ctx->h_perm[d];
   }
-  if (ns) NS_CUDA(ctx, cudaMemcpy(h.d_send_idx, si.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
-  if (nr) NS_CUDA(ctx, cudaMemcpy(h.d_recv_idx, ri.data(), sizeof(int32_t) * nr, cudaMemcpyHostToDevice));
+  if (ns) NS_CUDA(ctx, h2d_sync(ctx, h.d_send_idx, si.data(), sizeof(int32_t) * ns));
+  if (nr) NS_CUDA(ctx, h2d_sync(ctx, h.d_recv_idx, ri.data(), sizeof(int32_t) * nr));
   return NSGPU_OK;
 }
 
@@ -247,7 +247,7 @@ extern "C" int nsgpu_set_row_exchange(nsgpu_ctx* ctx, int n_neigh, const int32_t
     if ((rc = translate_positions(ctx, nr, recv_pos, r.d_recv_pos))) return rc;
     return NSGPU_OK;
   }
-  if (ns) NS_CUDA(ctx, cudaMemcpy(r.d_send_pos, send_pos, sizeof(int64_t) * ns, cudaMemcpyHostToDevice));
-  if (nr) NS_CUDA(ctx, cudaMemcpy(r.d_recv_pos, recv_pos, sizeof(int64_t) * nr, cudaMemcpyHostToDevice));
+  if (ns) NS_CUDA(ctx, h2d_sync(ctx, r.d_send_pos, send_pos, sizeof(int64_t) * ns));
+  if (nr) NS_CUDA(ctx, h2d_sync(ctx, r.d_recv_pos, recv_pos, sizeof(int64_t) * nr));
   return NSGPU_OK;
 }

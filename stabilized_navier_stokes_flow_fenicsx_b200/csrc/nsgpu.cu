@@ -185,8 +185,8 @@ int nsgpu_set_mesh(nsgpu_ctx* ctx, int gdim, int64_t n_nodes, const double* x, i
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_x, n_nodes * 3))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_cells, n_cells_total * (gdim + 1)))) return rc;
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_x, x, sizeof(double) * n_nodes * 3, cudaMemcpyHostToDevice));
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_cells, x_dofmap, sizeof(int32_t) * n_cells_total * (gdim + 1), cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_x, x, sizeof(double) * n_nodes * 3));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_cells, x_dofmap, sizeof(int32_t) * n_cells_total * (gdim + 1)));
   return NSGPU_OK;
 }
 
@@ -208,16 +208,16 @@ int nsgpu_set_space(nsgpu_ctx* ctx, int vdeg, const int32_t* dofmap, int64_t n_d
   ctx->has_bc = false;
   int rc;
   if ((rc = dev_alloc(ctx, &ctx->d_dofmap, ctx->n_cells_total * ctx->nd))) return rc;
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_dofmap, dofmap, sizeof(int32_t) * ctx->n_cells_total * ctx->nd, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_dofmap, dofmap, sizeof(int32_t) * ctx->n_cells_total * ctx->nd));
   if ((rc = dev_alloc(ctx, &ctx->d_xvec, ctx->n_dofs))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_F, ctx->n_dofs))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_y, ctx->n_dofs))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_bc_marker, ctx->n_dofs))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_bc_value, ctx->n_dofs))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_bc_mult, ctx->n_dofs))) return rc;
-  NS_CUDA(ctx, cudaMemset(ctx->d_bc_marker, 0, ctx->n_dofs));
-  NS_CUDA(ctx, cudaMemset(ctx->d_bc_value, 0, sizeof(double) * ctx->n_dofs));
-  NS_CUDA(ctx, cudaMemset(ctx->d_bc_mult, 0, sizeof(int32_t) * ctx->n_dofs));
+  NS_CUDA(ctx, cudaMemsetAsync(ctx->d_bc_marker, 0, ctx->n_dofs, ctx->stream));
+  NS_CUDA(ctx, cudaMemsetAsync(ctx->d_bc_value, 0, sizeof(double) * ctx->n_dofs, ctx->stream));
+  NS_CUDA(ctx, cudaMemsetAsync(ctx->d_bc_mult, 0, sizeof(int32_t) * ctx->n_dofs, ctx->stream));
   // internal vertex-blocked numbering for the P1-P1 tetrahedron space when the caller's is not (renumber.cu); from here on
   // ctx->d_dofmap and everything derived from it live in the internal numbering
   return renumber_build(ctx);
@@ -256,9 +256,9 @@ int nsgpu_set_bcs(nsgpu_ctx* ctx, int n_bc, const int64_t* bc_ptr, const int32_t
   }
   ctx->has_bc = total > 0;
   p1tet_mark_bc_dirty(ctx);
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_marker, marker.data(), ctx->n_dofs, cudaMemcpyHostToDevice));
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_value, value.data(), sizeof(double) * ctx->n_dofs, cudaMemcpyHostToDevice));
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_bc_mult, mult.data(), sizeof(int32_t) * ctx->n_dofs, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_bc_marker, marker.data(), ctx->n_dofs));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_bc_value, value.data(), sizeof(double) * ctx->n_dofs));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_bc_mult, mult.data(), sizeof(int32_t) * ctx->n_dofs));
   return NSGPU_OK;
 }
 
@@ -299,7 +299,7 @@ int nsgpu_set_col_ghosts(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_
   if ((rc = dev_alloc(ctx, &ctx->d_xvec, ctx->n_cols))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_y, ctx->n_cols))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_F, ctx->n_cols))) return rc;
-  NS_CUDA(ctx, cudaMemset(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols));
+  NS_CUDA(ctx, cudaMemsetAsync(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols, ctx->stream));
   return NSGPU_OK;
 }
 
@@ -590,12 +590,12 @@ int nsgpu_set_values(nsgpu_ctx* ctx, const double* vals) {
   if (permuted(ctx)) {
     int rc = caller_vals_buffer(ctx);
     if (rc) return rc;
-    NS_CUDA(ctx, cudaMemcpy(ctx->d_vals_c, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
+    NS_CUDA(ctx, h2d_sync(ctx, ctx->d_vals_c, vals, sizeof(double) * ctx->nnz));
     if ((rc = import_values(ctx, ctx->d_vals_c))) return rc;
     NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NSGPU_OK;
   }
-  NS_CUDA(ctx, cudaMemcpy(ctx->d_vals, vals, sizeof(double) * ctx->nnz, cudaMemcpyHostToDevice));
+  NS_CUDA(ctx, h2d_sync(ctx, ctx->d_vals, vals, sizeof(double) * ctx->nnz));
   return NSGPU_OK;
 }
 

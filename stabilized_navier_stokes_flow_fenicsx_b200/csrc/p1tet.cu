@@ -961,7 +961,7 @@ static int ws_build_tables(nsgpu_ctx* ctx) {
   int64_t total = 0;
   int flag = 1;
   if (e == cudaSuccess) {
-    k_ws_hsizes<<<g256(nt + 1), 256, 0, s>>>(nt, P->d_tile_hdr, P->d_ent_rel, P->d_tile_bytes, d_sz);
+    k_ws_hsizes<<<g256(nt + 1), 256, 0, s>>>(nt, P->d_tile_hdr, P->d_ent_rel, P->d_tile_bytes, d_sz, d_flag);
     size_t tb = 0;
     e = cub::DeviceScan::ExclusiveSum(nullptr, tb, d_sz, d_off, nt + 1, s);
     if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tb);
@@ -1147,7 +1147,7 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   h_tile_ent.push_back(n_ent);
   P->n_tiles = n_tiles;
   PL_CUDA(cudaMalloc(&d_tile_ent, sizeof(int64_t) * (n_tiles + 1)));
-  PL_CUDA(cudaMemcpy(d_tile_ent, h_tile_ent.data(), sizeof(int64_t) * (n_tiles + 1), cudaMemcpyHostToDevice));
+  PL_CUDA(h2d_sync(ctx, d_tile_ent, h_tile_ent.data(), sizeof(int64_t) * (n_tiles + 1)));
   PL_CUDA(cudaMalloc(&d_tsize, sizeof(int64_t) * (n_tiles + 1)));
   PL_CUDA(cudaMalloc(&d_boff, sizeof(int64_t) * (n_tiles + 1)));
   k_tile_sizes<<<g256(n_tiles + 1), 256, 0, s>>>(n_tiles, d_tile_ent, d_slot_ptr, d_tsize, d_flag + 2);

@@ -23,13 +23,19 @@ namespace nsgpu {
 constexpr int WS_SS = 120;         // incidence columns of a staging buffer: tiles are packed to <= WS_SS incidences
 constexpr int WS_VCAP = 96;        // distinct mesh vertices per tile (= bound on the total neighbour slots of a tile)
 constexpr int WS_NBUF = 3;
+#ifndef WS_REG_COMPUTE
+#define WS_REG_COMPUTE 216           // registers per thread of the compute warpgroups after setmaxnreg ...
+#define WS_REG_GATHER 72             // ... and of the gather warpgroup: 2 * 216 + 72 = 3 * 168 (the launch allocation of 384 threads)
+#endif
 constexpr int WS_CBLOB = 8 * WS_VCAP + 512 + 512 + 16;                                   // bytes per tile
-constexpr int WS_HMAX = 32 + 16 * TILE_MAX_ENT + 16 * WS_VCAP + 2 * (3 * WS_SS + WS_VCAP);   // largest H blob (multiple of 16)
+constexpr int WS_LIST = 8;          // gather-list entries held in the slot record itself (longer lists continue in the overflow area)
+constexpr int WS_OVF = 256;         // overflow entries per tile
+constexpr int WS_HMAX = 32 + 16 * TILE_MAX_ENT + 32 * WS_VCAP + 2 * WS_OVF;   // largest H blob (multiple of 16)
 static_assert(WS_HMAX % 16 == 0 && WS_CBLOB % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 struct WsHdr { int nent, ninc, n_off, pad0; int64_t vbase; int64_t pad1; };                    // 32 bytes
 struct WsVrec { uint16_t ib, ie; uint32_t diag_off; uint32_t rowlen; int32_t dof0; };          // 16 bytes: incidences [ib, ie) of the tile
-struct WsSrec { uint16_t list_off, len; uint32_t out_off; uint32_t rowlen; uint32_t pad; };    // 16 bytes: list = u16 staging indices
+struct WsSrec { uint16_t len, ovf; uint32_t out_off; uint32_t rowlen; uint32_t pad; uint16_t list[WS_LIST]; };   // 32 bytes: list = u16 staging indices
 
 template <bool WANT_J> struct WsSmem {
   static constexpr size_t stage = (WANT_J ? (size_t)32 * WS_SS * sizeof(double2) : 0) + (size_t)WS_SS * sizeof(double4);
@@ -44,7 +50,7 @@ static_assert(WsSmem<true>::bytes <= 232448, "staging ring + tables must fit the
 
 // ------------------------------------------------------------------------------------------ plan tables
 __global__ void k_ws_hsizes(int64_t n_tiles, const TileHdr* __restrict__ hdr, const int2* __restrict__ ent_rel, const uint8_t* __restrict__ tile_bytes,
-                            int64_t* sizes) {
+                            int64_t* sizes, int* flags) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   if (t == n_tiles) { sizes[t] = 0; return; }
@@ -52,17 +58,18 @@ __global__ void k_ws_hsizes(int64_t n_tiles, const TileHdr* __restrict__ hdr, co
   const uint8_t* s_ss = tile_bytes + h.boff;
   const uint8_t* eos = s_ss + pad16(h.nslots + h.nent + 1);
   const uint8_t* dg = eos + pad16(h.nslots);
-  int items = 0;
+  int ovf = 0;
   for (int ls = 0; ls < h.nslots; ++ls) {
     const int le = eos[ls];
     const int s = ls - ent_rel[h.e0 + le].y;
     if (s == dg[le]) continue;
     const uint8_t* ss = s_ss + ls + le;
     const int len = (int)ss[1] - (int)ss[0];
-    items += (len + 1) & ~1;
+    if (len > WS_LIST) ovf += len - WS_LIST;
   }
+  if (ovf > WS_OVF) flags[0] = 1;
   const int n_off = h.nslots - h.nent;
-  sizes[t] = h.nent > 0 ? ((32 + 16 * h.nent + 16 * n_off + 2 * items + 15) & ~15) : 32;
+  sizes[t] = h.nent > 0 ? ((32 + 16 * h.nent + 32 * n_off + 2 * ovf + 15) & ~15) : 32;
 }
 
 // one CTA per tile: header, vertex records, off-diagonal slot records and their gather lists as staging indices
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(128) k_ws_hfill(const TileHdr* __restrict__ hd
   const int64_t vbase = rowpos[4 * h.e0];
   WsVrec* vrec = reinterpret_cast<WsVrec*>(B + 32);
   WsSrec* srec = reinterpret_cast<WsSrec*>(B + 32 + 16 * h.nent);
-  uint16_t* lists = reinterpret_cast<uint16_t*>(B + 32 + 16 * h.nent + 16 * n_off);
+  uint16_t* ovf = reinterpret_cast<uint16_t*>(B + 32 + 16 * h.nent + 32 * n_off);
   if (tid == 0) {
     WsHdr w;
     w.nent = h.nent; w.ninc = h.ninc; w.n_off = n_off; w.pad0 = 0; w.vbase = vbase; w.pad1 = 0;
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(128) k_ws_hfill(const TileHdr* __restrict__ hd
   }
   const uint8_t* srcb = reinterpret_cast<const uint8_t*>(p_src + t * 128);
   // two slots per thread (a tile has at most WS_VCAP <= 256 slots in total)
-  int len2[2] = {0, 0}, pos[2], total = 0;
+  int extra[2] = {0, 0}, pos[2], total = 0;
   int le_[2], s_[2], jb_[2], ln_[2];
   bool off_[2];
 #pragma unroll
@@ -125,11 +132,11 @@ __global__ void __launch_bounds__(128) k_ws_hfill(const TileHdr* __restrict__ hd
         vrec[le] = v;
       } else {
         off_[k] = true;
-        len2[k] = (ln_[k] + 1) & ~1;
+        extra[k] = ln_[k] > WS_LIST ? ln_[k] - WS_LIST : 0;
       }
     }
   }
-  Scan(tmp).ExclusiveSum(len2, pos, total);
+  Scan(tmp).ExclusiveSum(extra, pos, total);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     if (!off_[k]) continue;
@@ -139,15 +146,18 @@ __global__ void __launch_bounds__(128) k_ws_hfill(const TileHdr* __restrict__ hd
     const int64_t e = h.e0 + le;
     const int64_t rp0 = rowpos[4 * e], rl = rowpos[4 * e + 1] - rp0;
     WsSrec r;
-    r.list_off = (uint16_t)pos[k]; r.len = (uint16_t)ln_[k];
+    r.len = (uint16_t)ln_[k]; r.ovf = (uint16_t)pos[k];
     r.out_off = (uint32_t)(rp0 + 4 * s - vbase); r.rowlen = (uint32_t)rl; r.pad = 0;
-    srec[j] = r;
     const uint8_t* sp = srcb + 4 * rel.x + jb_[k];
-    for (int q = 0; q < ln_[k]; ++q) {
-      const int code = sp[q];
-      lists[pos[k] + q] = (uint16_t)((code & 3) * 8 * WS_SS + rel.x + (code >> 2));
+    for (int q = 0; q < WS_LIST; ++q) {
+      const int code = q < ln_[k] ? sp[q] : 0;
+      r.list[q] = q < ln_[k] ? (uint16_t)((code & 3) * 8 * WS_SS + rel.x + (code >> 2)) : (uint16_t)0;
     }
-    if (ln_[k] & 1) lists[pos[k] + ln_[k]] = 0;
+    srec[j] = r;
+    for (int q = WS_LIST; q < ln_[k]; ++q) {
+      const int code = sp[q];
+      ovf[pos[k] + q - WS_LIST] = (uint16_t)((code & 3) * 8 * WS_SS + rel.x + (code >> 2));
+    }
   }
 }
 
@@ -161,8 +171,7 @@ __global__ void k_ws_order(int64_t n_tiles, const uint64_t* __restrict__ hword, 
   uint8_t* B = hblob + ((hword[t] >> 16) << 4);
   if ((hword[t] & 0xffff) < 3) return;
   const WsHdr h = *reinterpret_cast<const WsHdr*>(B);
-  const WsSrec* srec = reinterpret_cast<const WsSrec*>(B + 32 + 16 * h.nent);
-  uint16_t* lists = reinterpret_cast<uint16_t*>(B + 32 + 16 * h.nent + 16 * h.n_off);
+  WsSrec* srec = reinterpret_cast<WsSrec*>(B + 32 + 16 * h.nent);
   for (int g = threadIdx.x; g * 8 < h.n_off; g += blockDim.x) {
     uint16_t* lst[8]; int len[8];
     int maxlen = 0;
@@ -170,8 +179,8 @@ __global__ void k_ws_order(int64_t n_tiles, const uint64_t* __restrict__ hword, 
       const int j = g * 8 + l;
       len[l] = 0; lst[l] = nullptr;
       if (j >= h.n_off) continue;
-      lst[l] = lists + srec[j].list_off;
-      len[l] = srec[j].len;
+      lst[l] = srec[j].list;
+      len[l] = srec[j].len < WS_LIST ? srec[j].len : WS_LIST;   // the overflow tail (rare) keeps its order
       maxlen = max(maxlen, len[l]);
     }
     for (int pos = 0; pos < maxlen; ++pos) {
@@ -280,55 +289,68 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // named barriers: FULL[b] = 1 + b, EMPTY[b] = 4 + b (256 threads: one compute group + the gather group), compute group g: 7 + g, gather group: 9
 struct WsView { double2* stageJ; double4* stageF; };
 
-// phase B of one tile by the 128 threads of the gather warpgroup
+// phase B of one tile by the 128 threads of the gather warpgroup.  One warp of the group runs alone on its SM sub-partition
+// next to two algebra warps, so its own latencies are not hidden by other gather warps: every work item is written as
+// straight-line code -- record and list arrive with two independent loads, then all block pieces of the item are requested
+// (predicated by the list length) before the first add.  Items: off-diagonal slot groups (eight consecutive slots x four rows)
+// and vertices (diagonal block + residual: four rows x eight incidence lanes), dealt round-robin to the four warps.
 template <bool WANT_J, bool WANT_F>
 __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, const double2* __restrict__ stageJ, const double4* __restrict__ stageF,
                                           const int tid, double* __restrict__ vals, double* __restrict__ F, const bool wide) {
-  const WsHdr h = *reinterpret_cast<const WsHdr*>(H);
-  const WsVrec* vrec = reinterpret_cast<const WsVrec*>(H + 32);
+  const int4 hd = *reinterpret_cast<const int4*>(H);                 // nent, ninc, n_off
+  const int64_t vbase = *reinterpret_cast<const int64_t*>(H + 16);
+  const int nent = hd.x, n_off = hd.z;
   const int lane = tid & 31, warp = tid >> 5;
-  if (WANT_J) {
-    // off-diagonal slots: a warp takes eight consecutive slots, lane = 8 * row + slot; every lane sums the two pieces of its
-    // row over the slot's 3-8 parked blocks and writes one finished 32-byte piece
-    const WsSrec* srec = reinterpret_cast<const WsSrec*>(H + 32 + 16 * h.nent);
-    const uint16_t* lists = reinterpret_cast<const uint16_t*>(H + 32 + 16 * h.nent + 16 * h.n_off);
-    const int r = lane >> 3;
-    const double2* base = stageJ + 2 * r * WS_SS;
-    for (int j = 8 * warp + (lane & 7); j < ((h.n_off + 7) & ~7); j += 32) {
-      if (j < h.n_off) {
-        const int4 sr = *reinterpret_cast<const int4*>(srec + j);
-        const int len = (unsigned)sr.x >> 16;
-        const uint32_t* lp = reinterpret_cast<const uint32_t*>(lists + (sr.x & 0xffff));
+  const int n_grp = WANT_J ? (n_off + 7) >> 3 : 0;
+  const int r = lane >> 3;
+  const double2* base = stageJ + 2 * r * WS_SS;
+  for (int item = warp; item < n_grp + nent; item += 4) {
+    if (item < n_grp) {
+      // ---- eight consecutive off-diagonal slots: lane = 8 * row + slot; the two pieces of the lane's row over the slot's blocks
+      const int j = 8 * item + (lane & 7);
+      if (j < n_off) {
+        const unsigned char* rec = H + 32 + 16 * nent + 32 * j;
+        const int4 sr = *reinterpret_cast<const int4*>(rec);           // len | ovf << 16, out_off, rowlen
+        const uint4 li = *reinterpret_cast<const uint4*>(rec + 16);     // eight staging indices
+        const int len = sr.x & 0xffff;
+        const uint32_t idx[8] = {li.x & 0xffff, li.x >> 16, li.y & 0xffff, li.y >> 16, li.z & 0xffff, li.z >> 16, li.w & 0xffff, li.w >> 16};
         double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
-        int q = 0;
-        for (; q + 1 < len; q += 2) {
-          const uint32_t two = lp[q >> 1];
-          const double2* b0 = base + (two & 0xffff);
-          const double2* b1 = base + (two >> 16);
-          const double2 a0 = b0[0], a1 = b0[WS_SS], c0 = b1[0], c1 = b1[WS_SS];
-          acc.x += a0.x + c0.x; acc.y += a0.y + c0.y; acc.z += a1.x + c1.x; acc.w += a1.y + c1.y;
+#pragma unroll
+        for (int q = 0; q < WS_LIST; ++q) {
+          if (q < len) {
+            const double2 a0 = base[idx[q]], a1 = base[idx[q] + WS_SS];
+            acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+          }
         }
-        if (q < len) {
-          const double2* b0 = base + (lp[q >> 1] & 0xffff);
-          const double2 a0 = b0[0], a1 = b0[WS_SS];
-          acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+        if (len > WS_LIST) {   // rare: an edge shared by more than eight cells
+          const uint16_t* ov = reinterpret_cast<const uint16_t*>(H + 32 + 16 * nent + 32 * n_off) + ((unsigned)sr.x >> 16);
+          for (int q = WS_LIST; q < len; ++q) {
+            const double2 a0 = base[ov[q - WS_LIST]], a1 = base[ov[q - WS_LIST] + WS_SS];
+            acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+          }
         }
-        store_piece(vals + h.vbase + (uint32_t)sr.y + (int64_t)r * (uint32_t)sr.z, acc, wide);
+        store_piece(vals + vbase + (uint32_t)sr.y + (int64_t)r * (uint32_t)sr.z, acc, wide);
       }
-    }
-  }
-  {
-    // diagonal block (block 0 of every incidence of the vertex) and the residual: a warp takes one vertex,
-    // lane = 8 * row + part, eight consecutive incidences per load round, then a butterfly over the parts
-    const int r = lane >> 3, part = lane & 7;
-    const double2* base = stageJ + 2 * r * WS_SS;
-    const double* sf = reinterpret_cast<const double*>(stageF);
-    for (int le = (3 - warp); le < h.nent; le += 4) {   // from the last warp: the first ones hold more slot groups
-      const int4 vr = *reinterpret_cast<const int4*>(vrec + le);
+    } else {
+      // ---- one vertex: diagonal block (block 0 of each of its incidences) and residual; lane = 8 * row + part
+      const int le = item - n_grp, part = lane & 7;
+      const int4 vr = *reinterpret_cast<const int4*>(H + 32 + 16 * le);
       const int ib = vr.x & 0xffff, ie = (unsigned)vr.x >> 16;
+      const double* sf = reinterpret_cast<const double*>(stageF);
       double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
       double accF = 0.0;
-      for (int i = ib + part; i < ie; i += 8) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = ib + part + 8 * t;
+        if (i < ie) {
+          if (WANT_J) {
+            const double2 a0 = base[i], a1 = base[WS_SS + i];
+            acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+          }
+          if (WANT_F) accF += sf[4 * i + r];
+        }
+      }
+      for (int i = ib + part + 32; i < ie; i += 8) {   // more than 32 incidences at one vertex
         if (WANT_J) {
           const double2 a0 = base[i], a1 = base[WS_SS + i];
           acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
@@ -344,7 +366,7 @@ __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, c
         if (WANT_F) accF += __shfl_xor_sync(0xffffffffu, accF, o);
       }
       if (part == 0) {
-        if (WANT_J) store_piece(vals + h.vbase + (uint32_t)vr.y + (int64_t)r * (uint32_t)vr.z, acc, wide);
+        if (WANT_J) store_piece(vals + vbase + (uint32_t)vr.y + (int64_t)r * (uint32_t)vr.z, acc, wide);
         if (WANT_F) F[vr.w + r] = accF;
       }
     }
@@ -369,7 +391,7 @@ k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* _
   __syncthreads();
   auto stage_of = [&](int b) { return smem_raw + (size_t)b * S::stage; };
   if (wg < 2) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
     const int g = wg;
     const int nm = nk > g ? (nk - g + 1) / 2 : 0;                                       // this group's tiles: k = g + 2 m
     unsigned char* ring = smem_raw + S::off_ring + (size_t)g * 2 * WS_CBLOB;
@@ -434,7 +456,7 @@ k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* _
       named_bar_arrive(1 + b, 256);          // FULL[b]
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_GATHER));
     unsigned char* htab = smem_raw + S::off_htab;
     auto word_of = [&](const int k) { return hword[tile0 + (int64_t)blockIdx.x + (int64_t)k * gridDim.x]; };
     auto fetch_h = [&](const int k, const uint64_t w) {   // one thread: H blob of tile k -> table buffer k % 3
