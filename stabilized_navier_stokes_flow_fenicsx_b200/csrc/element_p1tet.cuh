@@ -269,6 +269,9 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
 #pragma unroll
   for (int d = 0; d < 3; ++d) H[d] = D[d][0] * g[0][0] + D[d][1] * g[0][1] + D[d][2] * g[0][2];
   const double Pg0 = P[0] * g[0][0] + P[1] * g[0][1] + P[2] * g[0][2];
+  // the point loop needs neither grad u nor the gradients of the other three vertices: the caller may take them out of the
+  // register file until the block loop (shared-memory scratch in the kernels; a plain copy on the host)
+  scratch.put_geom(g, D);
 
   // ---- quadrature points: totals stay in registers, the data of points 1..3 is parked ----
   // (sum_q W tau r_q and sum_q W tau G u_q follow from s = sum_q W tau u_q after the loop: both are linear in u_q)
@@ -323,6 +326,7 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
   nuLbar *= itrG;
 
   const double TR0 = tbar * Pg0 + H[0] * s[0] + H[1] * s[1] + H[2] * s[2];   // (sum_q W tau r_q) . g_0
+  scratch.get_D(D);
 
   if (WANT_F) {
     const double pbarV = W * (p[0] + p[1] + p[2] + p[3]);
@@ -353,7 +357,7 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       P1TetPoint pt;
-      if (n == 0) pt = pt0; else scratch.get(n, pt);
+      if (n == 0) pt = pt0; else { scratch.get(n, pt); scratch.get_g(n, g[n]); }
       const double L = g[0][0] * g[n][0] + g[0][1] * g[n][1] + g[0][2] * g[n][2];
       double t1[3], t2[3];
       const double ewk = pt.ew * kap;

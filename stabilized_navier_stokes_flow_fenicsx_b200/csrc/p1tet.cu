@@ -640,8 +640,36 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
         int tid;
         Hook& hook;
         __device__ double after_geometry(double w) const { return w; }
+        // grad u (block 0, pieces 0..4: free until block 0 is emitted) and the gradients of vertices 1..3 (pieces 5, 6 of their
+        // blocks) leave the register file for the duration of the point loop; volatile accesses keep the compiler from
+        // forwarding the stored registers to the loads
+        __device__ void put_geom(const double (&g)[4][3], const double (&D)[3][3]) const {
+          hook();   // first write into the view
+          volatile double2* vs = st;
+          vs[stage_idx(CAP, 0, 0, tid)].x = D[0][0]; vs[stage_idx(CAP, 0, 0, tid)].y = D[0][1];
+          vs[stage_idx(CAP, 0, 1, tid)].x = D[0][2]; vs[stage_idx(CAP, 0, 1, tid)].y = D[1][0];
+          vs[stage_idx(CAP, 0, 2, tid)].x = D[1][1]; vs[stage_idx(CAP, 0, 2, tid)].y = D[1][2];
+          vs[stage_idx(CAP, 0, 3, tid)].x = D[2][0]; vs[stage_idx(CAP, 0, 3, tid)].y = D[2][1];
+          vs[stage_idx(CAP, 0, 4, tid)].x = D[2][2];
+#pragma unroll
+          for (int n = 1; n < 4; ++n) {
+            vs[stage_idx(CAP, n, 5, tid)].x = g[n][0]; vs[stage_idx(CAP, n, 5, tid)].y = g[n][1];
+            vs[stage_idx(CAP, n, 6, tid)].x = g[n][2];
+          }
+        }
+        __device__ void get_D(double (&D)[3][3]) const {
+          const volatile double2* vs = st;
+          D[0][0] = vs[stage_idx(CAP, 0, 0, tid)].x; D[0][1] = vs[stage_idx(CAP, 0, 0, tid)].y;
+          D[0][2] = vs[stage_idx(CAP, 0, 1, tid)].x; D[1][0] = vs[stage_idx(CAP, 0, 1, tid)].y;
+          D[1][1] = vs[stage_idx(CAP, 0, 2, tid)].x; D[1][2] = vs[stage_idx(CAP, 0, 2, tid)].y;
+          D[2][0] = vs[stage_idx(CAP, 0, 3, tid)].x; D[2][1] = vs[stage_idx(CAP, 0, 3, tid)].y;
+          D[2][2] = vs[stage_idx(CAP, 0, 4, tid)].x;
+        }
+        __device__ void get_g(int n, double (&gn)[3]) const {
+          const volatile double2* vs = st;
+          gn[0] = vs[stage_idx(CAP, n, 5, tid)].x; gn[1] = vs[stage_idx(CAP, n, 5, tid)].y; gn[2] = vs[stage_idx(CAP, n, 6, tid)].x;
+        }
         __device__ void put(int q, const P1TetPoint& pt) const {
-          if (q == 1) hook();   // first write into the view
           st[stage_idx(CAP, q, 0, tid)] = make_double2(pt.uq[0], pt.uq[1]); st[stage_idx(CAP, q, 1, tid)] = make_double2(pt.uq[2], pt.Gu[0]);
           st[stage_idx(CAP, q, 2, tid)] = make_double2(pt.Gu[1], pt.Gu[2]); st[stage_idx(CAP, q, 3, tid)] = make_double2(pt.ew, pt.eb);
           st[stage_idx(CAP, q, 4, tid)] = make_double2(pt.ea, 0.0);
@@ -659,6 +687,9 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
       struct LocalScratch {
         P1TetPoint q[4];
         __device__ double after_geometry(double w) const { return w; }
+        __device__ void put_geom(const double (&)[4][3], const double (&)[3][3]) const {}
+        __device__ void get_D(double (&)[3][3]) const {}
+        __device__ void get_g(int, double (&)[3]) const {}
         __device__ void put(int i, const P1TetPoint& pt) { q[i] = pt; }
         __device__ void get(int i, P1TetPoint& pt) const { pt = q[i]; }
       } scratch;

@@ -165,3 +165,16 @@ def test_ugn_zero_velocity_cell_is_finite(oracle):
     w[6:] = [0.3, -0.2, 0.5]
     Ae, be = oracle.element(form, x, w)
     assert np.isfinite(Ae).all() and np.isfinite(be).all()
+
+
+def test_oracle_reproduces_the_dfg_2d_1_reference_values(oracle):
+    """A pin that comes from the reference side: DFG_2D_Validation.py:202-203 holds Cd = 5.57953523384 and
+    Cl = 0.010618948146 for the UGN-stabilised P1-P1 solve of the 2D-1 benchmark.  The oracle's UGN form + dolfinx-semantics
+    assembly, driven by Newton on a 5 462-cell triangulation of the same domain, must land on them."""
+    import _pins as P
+    m, sp, bcs, obstacle = P.dfg_problem()
+    r = P.dfg_solve(P.OracleBackend(oracle, m, sp, bcs), sp, bcs, obstacle)
+    assert r["newton"][-1][1] < 1e-8, r["newton"]
+    assert abs(r["cd"] / P.DFG_CD - 1.0) < 0.01, r["cd"]
+    assert abs(r["cl"] / P.DFG_CL - 1.0) < 0.05, r["cl"]
+    assert abs(r["dp"] / P.DFG_DP - 1.0) < 0.04, r["dp"]
