@@ -276,6 +276,45 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   if (want_F) NS_CUDA(ctx, cudaMemsetAsync(d_Fout, 0, sizeof(double) * ctx->n_cols, s));                          // f_local.set(0.0)
   NS_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
 
+  // Several ranks: the tiles that hold ghost vertices are assembled first; packing and the NCCL send / receive of the ghost
+  // rows (J.assemble()) and of the ghost residual entries (F.ghostUpdate(ADD, REVERSE)) then run on a second stream while
+  // the interior tiles are assembled, and only the adds wait for both (NavierStokesChannelFlow.py:66, :75).
+  const bool split = fast && ctx->nranks > 1 && ctx->overlap && ctx->halo.n_neigh > 0 && p1tet_can_split(ctx);
+  if (split) {
+    if (!ctx->stream2) {
+      int lo = 0, hi = 0;
+      NS_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      NS_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+      NS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x[0], cudaEventDisableTiming));
+      NS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x[1], cudaEventDisableTiming));
+    }
+    int rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout, 1, 0);
+    if (rc != NSGPU_OK) return rc;
+    NS_CUDA(ctx, cudaEventRecord(ctx->ev_x[0], s));
+    NS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_x[0], 0));
+    if (want_J && (rc = rows_exchange_begin(ctx, ctx->stream2))) return rc;
+    if (want_F && (rc = halo_reverse_begin(ctx, d_Fout, ctx->stream2))) return rc;
+    NS_CUDA(ctx, cudaEventRecord(ctx->ev_x[1], ctx->stream2));
+    if ((rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout, 2, ctx->sm_reserve))) return rc;
+    NS_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+    NS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_x[1], 0));
+    if (want_J) {
+      if ((rc = rows_exchange_end(ctx))) return rc;
+      if (ctx->has_bc) {
+        k_bc_diagonal<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, s>>>(ctx->n_owned, ctx->d_bc_mult, ctx->d_diag, ctx->d_vals);
+        ctx->launches += 1;
+      }
+    }
+    if (want_F) {
+      if ((rc = halo_reverse_end(ctx, d_Fout))) return rc;
+      if (ctx->has_bc) {
+        k_set_bc<<<(unsigned)ceil_div(ctx->n_owned, 256), 256, 0, s>>>(ctx->n_owned, ctx->d_bc_marker, ctx->d_bc_value, d_xin, d_Fout);
+        ctx->launches += 1;
+      }
+    }
+    NS_CUDA(ctx, cudaGetLastError());
+    return NSGPU_OK;
+  }
   if (fast) {
     int rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout);
     if (rc != NSGPU_OK) return rc;

@@ -126,6 +126,10 @@ struct nsgpu_ctx {
   const char* last_kernel = "none";   // which assembly variant the last call used (nsgpu_last_kernel_name)
 
   // multi-GPU
+  int overlap = 1;          // option: ghost-row tiles first, then their exchanges run on a second stream beside the interior tiles
+  int sm_reserve = 4;       // SMs the interior launch leaves to the exchange kernels (a persistent grid would starve them otherwise)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_x[2] = {nullptr, nullptr};
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
   nsgpu::HaloPlan halo;
@@ -180,6 +184,10 @@ int dfma_peak_impl(nsgpu_ctx* ctx, double* tflops);
 int halo_forward(nsgpu_ctx* ctx, double* d_v);
 int halo_reverse_add(nsgpu_ctx* ctx, double* d_v);
 int rows_exchange_add(nsgpu_ctx* ctx);
+int halo_reverse_begin(nsgpu_ctx* ctx, double* d_v, cudaStream_t stream);
+int halo_reverse_end(nsgpu_ctx* ctx, double* d_v);
+int rows_exchange_begin(nsgpu_ctx* ctx, cudaStream_t stream);
+int rows_exchange_end(nsgpu_ctx* ctx);
 void halo_free(nsgpu_ctx* ctx);
 int allreduce_sum(nsgpu_ctx* ctx, double* d_buf, int n);
 // krylov.cu

@@ -391,7 +391,8 @@ NS_HD void p1tet_rowslab2(const FormParams& fp, const bool row_is_origin, const 
 struct nsgpu_ctx;
 namespace nsgpu {
 bool p1tet_fast_available(nsgpu_ctx* ctx);
-int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);
+int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int part = 0, int sm_reserve = 0);
+bool p1tet_can_split(nsgpu_ctx* ctx);
 int p1tet_build_plan(nsgpu_ctx* ctx);
 void p1tet_free(nsgpu_ctx* ctx);
 void p1tet_mark_bc_dirty(nsgpu_ctx* ctx);

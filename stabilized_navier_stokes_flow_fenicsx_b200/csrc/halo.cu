@@ -85,7 +85,8 @@ static inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n > 0 ? n : 1
 
 // exchange: send sbuf segments (sptr) to neighbours, receive rbuf segments (rptr)
 static int exchange(nsgpu_ctx* ctx, const std::vector<int>& ranks, const std::vector<int64_t>& sptr, const double* sbuf,
-                    const std::vector<int64_t>& rptr, double* rbuf) {
+                    const std::vector<int64_t>& rptr, double* rbuf, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   std::string why;
   NcclApi* api = nccl_api(&why);
   if (!api || !ctx->nccl_comm) { set_error(ctx, "halo exchange without a communicator"); return NSGPU_ENCCL; }
@@ -93,8 +94,8 @@ static int exchange(nsgpu_ctx* ctx, const std::vector<int>& ranks, const std::ve
   NS_NCCL(ctx, api, api->GroupStart());
   for (size_t k = 0; k < ranks.size(); ++k) {
     const int64_t ns = sptr[k + 1] - sptr[k], nr = rptr[k + 1] - rptr[k];
-    if (ns > 0) NS_NCCL(ctx, api, api->Send(sbuf + sptr[k], (size_t)ns, ncclFloat64, ranks[k], comm, ctx->stream));
-    if (nr > 0) NS_NCCL(ctx, api, api->Recv(rbuf + rptr[k], (size_t)nr, ncclFloat64, ranks[k], comm, ctx->stream));
+    if (ns > 0) NS_NCCL(ctx, api, api->Send(sbuf + sptr[k], (size_t)ns, ncclFloat64, ranks[k], comm, stream));
+    if (nr > 0) NS_NCCL(ctx, api, api->Recv(rbuf + rptr[k], (size_t)nr, ncclFloat64, ranks[k], comm, stream));
   }
   NS_NCCL(ctx, api, api->GroupEnd());
   return NSGPU_OK;
@@ -133,6 +134,39 @@ int halo_reverse_add(nsgpu_ctx* ctx, double* d_v) {
   int rc = exchange(ctx, h.rank, h.recv_ptr, h.d_recv_buf, h.send_ptr, h.d_send_buf);
   if (rc != NSGPU_OK) return rc;
   if (ns) { k_scatter_add<<<g256(ns), 256, 0, s>>>(ns, h.d_send_idx, h.d_send_buf, d_v); ctx->launches++; }
+  NS_CUDA(ctx, cudaGetLastError());
+  return NSGPU_OK;
+}
+
+// the two halves of F.ghostUpdate(ADD, REVERSE) and of J.assemble() for the overlapped assembly (assemble.cu): pack + send /
+// receive on `stream`, add on the context's stream once the local rows are final
+int halo_reverse_begin(nsgpu_ctx* ctx, double* d_v, cudaStream_t stream) {
+  HaloPlan& h = ctx->halo;
+  if (ctx->nranks <= 1 || h.n_neigh == 0) return NSGPU_OK;
+  const int64_t nr = h.recv_ptr.back();
+  if (nr) { k_gather<<<g256(nr), 256, 0, stream>>>(nr, h.d_recv_idx, d_v, h.d_recv_buf); ctx->launches++; }
+  return exchange(ctx, h.rank, h.recv_ptr, h.d_recv_buf, h.send_ptr, h.d_send_buf, stream);
+}
+int halo_reverse_end(nsgpu_ctx* ctx, double* d_v) {
+  HaloPlan& h = ctx->halo;
+  if (ctx->nranks <= 1 || h.n_neigh == 0) return NSGPU_OK;
+  const int64_t ns = h.send_ptr.back();
+  if (ns) { k_scatter_add<<<g256(ns), 256, 0, ctx->stream>>>(ns, h.d_send_idx, h.d_send_buf, d_v); ctx->launches++; }
+  NS_CUDA(ctx, cudaGetLastError());
+  return NSGPU_OK;
+}
+int rows_exchange_begin(nsgpu_ctx* ctx, cudaStream_t stream) {
+  RowPlan& r = ctx->rows;
+  if (ctx->nranks <= 1 || r.n_neigh == 0) return NSGPU_OK;
+  const int64_t ns = r.send_ptr.back();
+  if (ns) { k_gather64<<<g256(ns), 256, 0, stream>>>(ns, r.d_send_pos, ctx->d_vals, r.d_send_buf); ctx->launches++; }
+  return exchange(ctx, r.rank, r.send_ptr, r.d_send_buf, r.recv_ptr, r.d_recv_buf, stream);
+}
+int rows_exchange_end(nsgpu_ctx* ctx) {
+  RowPlan& r = ctx->rows;
+  if (ctx->nranks <= 1 || r.n_neigh == 0) return NSGPU_OK;
+  const int64_t nr = r.recv_ptr.back();
+  if (nr) { k_scatter_add64<<<g256(nr), 256, 0, ctx->stream>>>(nr, r.d_recv_pos, r.d_recv_buf, ctx->d_vals); ctx->launches++; }
   NS_CUDA(ctx, cudaGetLastError());
   return NSGPU_OK;
 }

@@ -152,6 +152,9 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   krylov_free(ctx);
   renumber_free(ctx);
   cudaFree(ctx->d_nonfinite);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_x[0]) cudaEventDestroy(ctx->ev_x[0]);
+  if (ctx->ev_x[1]) cudaEventDestroy(ctx->ev_x[1]);
   cudaFree(ctx->d_x_last);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -691,6 +694,11 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {
     ctx->pipe = value != 0;
+  } else if (!strcmp(name, "overlap")) {
+    ctx->overlap = value != 0;
+  } else if (!strcmp(name, "sm_reserve")) {
+    NS_REQUIRE(ctx, value >= 0 && value <= 64, "set_option: sm_reserve must be 0..64");
+    ctx->sm_reserve = (int)value;
   } else if (!strcmp(name, "check_finite")) {
     ctx->check_finite = value != 0;
   } else if (!strcmp(name, "renumber")) {

@@ -71,6 +71,7 @@ struct nsgpu_p1tet_plan {
   uint8_t* d_hblob = nullptr;       // per tile: header | vertex records | slot records | gather lists
   uint64_t* d_hword = nullptr;      // [n_tiles] (offset / 16) << 16 | (size / 16) of the tile's H blob
   bool ws_ok = false;
+  int64_t t_ghost = -1;             // first tile that holds a ghost vertex (rows shipped to another rank); n_tiles when there is none
   bool ws_attr = false;             // kernel attributes set on this context's device
   int pipe_occ = 0;                 // resident CTAs per SM of the pipelined kernel on this context's device
   bool bc_dirty = true;
@@ -975,6 +976,15 @@ template <typename K> static cudaError_t smem_attr(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// first tile whose vertices include a ghost (leader dof >= n_owned): vertices are sorted by leader, so ghost tiles are a suffix
+__global__ void k_first_ghost_tile(int64_t n_tiles, const TileHdr* __restrict__ hdr, const int32_t* __restrict__ rowdof, int64_t n_owned,
+                                   unsigned long long* out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const TileHdr h = hdr[t];
+  if (h.nent > 0 && rowdof[4 * (h.e0 + h.nent - 1)] >= n_owned) atomicMin(out, (unsigned long long)t);
+}
+
 // per-tile blobs of the warp-specialised kernel (p1tet_ws.cuh), from the finished tile tables of the plan
 static int ws_build_tables(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
@@ -1222,6 +1232,19 @@ int p1tet_build_plan(nsgpu_ctx* ctx) {
   P->rows32 = flags[4] == 0;
   P->bc_dirty = true;
   ctx->p1plan = P;
+  {
+    unsigned long long* d_tg = nullptr;
+    unsigned long long tg = (unsigned long long)P->n_tiles;
+    if (cudaMalloc(&d_tg, sizeof(unsigned long long)) == cudaSuccess) {
+      cudaMemcpyAsync(d_tg, &tg, sizeof(tg), cudaMemcpyHostToDevice, s);
+      k_first_ghost_tile<<<g256(P->n_tiles), 256, 0, s>>>(P->n_tiles, P->d_tile_hdr, P->d_rowdof, ctx->n_owned, d_tg);
+      cudaMemcpyAsync(&tg, d_tg, sizeof(tg), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      cudaFree(d_tg);
+      ctx->launches += 1;
+    }
+    P->t_ghost = (int64_t)tg;
+  }
   if (P->contiguous && P->d_tile_vlist && P->max_nv <= WS_VCAP && P->max_nent <= TILE_MAX_ENT) {
     int rc = ws_build_tables(ctx);
     if (rc != NSGPU_OK) { p1tet_free(ctx); return rc; }
@@ -1241,7 +1264,7 @@ static bool ws_applies(nsgpu_ctx* ctx) {
 }
 
 // warp-specialised persistent kernel, one 384-thread CTA per SM, over the tiles [t0, t1)
-static int ws_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1) {
+static int ws_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1, int sm_reserve = 0) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P->ws_attr) {
     NS_CUDA(ctx, cudaFuncSetAttribute(k_p1tet_ws<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem<true>::bytes));
@@ -1251,7 +1274,8 @@ static int ws_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want
   }
   const int64_t nt = t1 - t0;
   if (nt <= 0) return NSGPU_OK;
-  const unsigned grid = (unsigned)(ctx->n_sms < nt ? ctx->n_sms : nt);
+  const int64_t sms = ctx->n_sms - sm_reserve > 8 ? ctx->n_sms - sm_reserve : ctx->n_sms;   // SMs left to the copy / NCCL kernels of an overlapped exchange
+  const unsigned grid = (unsigned)(sms < nt ? sms : nt);
 #define P1_WS_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_bc_marker, ctx->d_bc_value, P->d_cblob, P->d_hblob, P->d_hword, ctx->d_vals, d_Fout, nt, t0, P->rows32
   if (want_J && want_F) k_p1tet_ws<true, true><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
   else if (want_J) k_p1tet_ws<true, false><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
@@ -1267,7 +1291,7 @@ static bool pipe_applies(nsgpu_ctx* ctx) {
 }
 
 // software-pipelined persistent kernel, 2 CTAs/SM, over the tiles [t0, t1)
-static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1) {
+static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int64_t t0, int64_t t1, int sm_reserve = 0) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   cudaStream_t s = ctx->stream;
   int& pipe_occ = P->pipe_occ;   // resident CTAs per SM (the two J kernels need the full shared-memory carve-out for 2); per context = per device
@@ -1285,7 +1309,7 @@ static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool wa
   }
   const int64_t nt = t1 - t0;
   if (nt <= 0) return NSGPU_OK;
-  const int64_t resident = (int64_t)pipe_occ * ctx->n_sms;
+  const int64_t resident = (int64_t)pipe_occ * (ctx->n_sms - sm_reserve > 8 ? ctx->n_sms - sm_reserve : ctx->n_sms);
   const unsigned grid = (unsigned)(resident < nt ? resident : nt);
 #define P1_PIPE_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, P->d_inc_vtx, \
                      P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof),         \
@@ -1297,7 +1321,14 @@ static int pipe_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool wa
   return NSGPU_OK;
 }
 
-int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout) {
+// can the assembly run as "ghost-row tiles first, interior tiles second" (overlapped exchanges, assemble.cu)?
+bool p1tet_can_split(nsgpu_ctx* ctx) {
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  return P && (ws_applies(ctx) || pipe_applies(ctx)) && P->t_ghost >= 0 && P->t_ghost < P->n_tiles;
+}
+
+// part 0: all tiles; part 1: the tiles that hold ghost vertices; part 2: the others, on n_sms - sm_reserve SMs
+int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout, int part, int sm_reserve) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
   if (!P) { set_error(ctx, "p1tet plan missing"); return NSGPU_EINVAL; }
   cudaStream_t s = ctx->stream;
@@ -1308,9 +1339,10 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
     P->bc_dirty = false;
     ctx->launches += 2;
   }
+  const int64_t t0 = part == 1 ? P->t_ghost : 0, t1 = part == 2 ? P->t_ghost : P->n_tiles;
   if (ws_applies(ctx)) {
     ctx->last_kernel = "p1tet_ws";
-    int rc = ws_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
+    int rc = ws_launch(ctx, d_xin, want_J, want_F, d_Fout, t0, t1, sm_reserve);
     if (rc != NSGPU_OK) return rc;
     ctx->launches += 1;
     NS_CUDA(ctx, cudaGetLastError());
@@ -1318,12 +1350,13 @@ int p1tet_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F
   }
   if (pipe_applies(ctx)) {
     ctx->last_kernel = "p1tet_pipe";
-    int rc = pipe_launch(ctx, d_xin, want_J, want_F, d_Fout, 0, P->n_tiles);
+    int rc = pipe_launch(ctx, d_xin, want_J, want_F, d_Fout, t0, t1, sm_reserve);
     if (rc != NSGPU_OK) return rc;
     ctx->launches += 1;
     NS_CUDA(ctx, cudaGetLastError());
     return NSGPU_OK;
   }
+  if (part != 0) { set_error(ctx, "split assembly needs the warp-specialised or the pipelined kernel"); return NSGPU_EINVAL; }
 #define P1_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_members, P->contiguous, ctx->d_bc_marker, ctx->d_bc_value, P->d_inc_cell, \
                 P->d_inc_vtx, P->d_inc_lead, P->d_src, P->d_tile_bytes, P->d_ent_rel, P->d_rowpos,                                  \
                 reinterpret_cast<const int4*>(P->d_rowdof), P->d_tile_hdr, ctx->d_vals, d_Fout, P->n_tiles
