@@ -646,29 +646,34 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
         // forwarding the stored registers to the loads
         __device__ void put_geom(const double (&g)[4][3], const double (&D)[3][3]) const {
           hook();   // first write into the view
-          volatile double2* vs = st;
-          vs[stage_idx(CAP, 0, 0, tid)].x = D[0][0]; vs[stage_idx(CAP, 0, 0, tid)].y = D[0][1];
-          vs[stage_idx(CAP, 0, 1, tid)].x = D[0][2]; vs[stage_idx(CAP, 0, 1, tid)].y = D[1][0];
-          vs[stage_idx(CAP, 0, 2, tid)].x = D[1][1]; vs[stage_idx(CAP, 0, 2, tid)].y = D[1][2];
-          vs[stage_idx(CAP, 0, 3, tid)].x = D[2][0]; vs[stage_idx(CAP, 0, 3, tid)].y = D[2][1];
-          vs[stage_idx(CAP, 0, 4, tid)].x = D[2][2];
+          sts2(stage_idx(CAP, 0, 0, tid), D[0][0], D[0][1]); sts2(stage_idx(CAP, 0, 1, tid), D[0][2], D[1][0]);
+          sts2(stage_idx(CAP, 0, 2, tid), D[1][1], D[1][2]); sts2(stage_idx(CAP, 0, 3, tid), D[2][0], D[2][1]);
+          sts2(stage_idx(CAP, 0, 4, tid), D[2][2], g[1][2]); sts2(stage_idx(CAP, 0, 5, tid), g[2][2], g[3][2]);
 #pragma unroll
-          for (int n = 1; n < 4; ++n) {
-            vs[stage_idx(CAP, n, 5, tid)].x = g[n][0]; vs[stage_idx(CAP, n, 5, tid)].y = g[n][1];
-            vs[stage_idx(CAP, n, 6, tid)].x = g[n][2];
-          }
+          for (int n = 1; n < 4; ++n) sts2(stage_idx(CAP, n, 5, tid), g[n][0], g[n][1]);
         }
         __device__ void get_D(double (&D)[3][3]) const {
-          const volatile double2* vs = st;
-          D[0][0] = vs[stage_idx(CAP, 0, 0, tid)].x; D[0][1] = vs[stage_idx(CAP, 0, 0, tid)].y;
-          D[0][2] = vs[stage_idx(CAP, 0, 1, tid)].x; D[1][0] = vs[stage_idx(CAP, 0, 1, tid)].y;
-          D[1][1] = vs[stage_idx(CAP, 0, 2, tid)].x; D[1][2] = vs[stage_idx(CAP, 0, 2, tid)].y;
-          D[2][0] = vs[stage_idx(CAP, 0, 3, tid)].x; D[2][1] = vs[stage_idx(CAP, 0, 3, tid)].y;
-          D[2][2] = vs[stage_idx(CAP, 0, 4, tid)].x;
+          double t;
+          lds2(stage_idx(CAP, 0, 0, tid), D[0][0], D[0][1]); lds2(stage_idx(CAP, 0, 1, tid), D[0][2], D[1][0]);
+          lds2(stage_idx(CAP, 0, 2, tid), D[1][1], D[1][2]); lds2(stage_idx(CAP, 0, 3, tid), D[2][0], D[2][1]);
+          lds2(stage_idx(CAP, 0, 4, tid), D[2][2], t);
+          // the z components of the three parked gradients ride in block 0's pieces 4 and 5, which block 0 overwrites when it is
+          // emitted: move them next to the x / y components (piece 6 of their own blocks)
+          double g2, g3;
+          lds2(stage_idx(CAP, 0, 5, tid), g2, g3);
+          sts2(stage_idx(CAP, 1, 6, tid), t, 0.0); sts2(stage_idx(CAP, 2, 6, tid), g2, 0.0); sts2(stage_idx(CAP, 3, 6, tid), g3, 0.0);
         }
         __device__ void get_g(int n, double (&gn)[3]) const {
-          const volatile double2* vs = st;
-          gn[0] = vs[stage_idx(CAP, n, 5, tid)].x; gn[1] = vs[stage_idx(CAP, n, 5, tid)].y; gn[2] = vs[stage_idx(CAP, n, 6, tid)].x;
+          double pad;
+          lds2(stage_idx(CAP, n, 5, tid), gn[0], gn[1]);
+          lds2(stage_idx(CAP, n, 6, tid), gn[2], pad);
+        }
+        // 128-bit shared accesses the compiler neither widens, splits nor forwards from registers
+        __device__ void sts2(int idx, double a, double b) const {
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(st + idx)), "d"(a), "d"(b) : "memory");
+        }
+        __device__ void lds2(int idx, double& a, double& b) const {
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned)__cvta_generic_to_shared(st + idx)) : "memory");
         }
         __device__ void put(int q, const P1TetPoint& pt) const {
           st[stage_idx(CAP, q, 0, tid)] = make_double2(pt.uq[0], pt.uq[1]); st[stage_idx(CAP, q, 1, tid)] = make_double2(pt.uq[2], pt.Gu[0]);
