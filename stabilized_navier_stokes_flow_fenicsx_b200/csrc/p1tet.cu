@@ -1282,9 +1282,9 @@ static int ws_launch(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want
   const int64_t sms = ctx->n_sms - sm_reserve > 8 ? ctx->n_sms - sm_reserve : ctx->n_sms;   // SMs left to the copy / NCCL kernels of an overlapped exchange
   const unsigned grid = (unsigned)(sms < nt ? sms : nt);
 #define P1_WS_ARGS ctx->form, ctx->d_x, d_xin, ctx->d_bc_marker, ctx->d_bc_value, P->d_cblob, P->d_hblob, P->d_hword, ctx->d_vals, d_Fout, nt, t0, P->rows32
-  if (want_J && want_F) k_p1tet_ws<true, true><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
-  else if (want_J) k_p1tet_ws<true, false><<<grid, 384, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
-  else k_p1tet_ws<false, true><<<grid, 384, WsSmem<false>::bytes, ctx->stream>>>(P1_WS_ARGS);
+  if (want_J && want_F) k_p1tet_ws<true, true><<<grid, 512, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
+  else if (want_J) k_p1tet_ws<true, false><<<grid, 512, WsSmem<true>::bytes, ctx->stream>>>(P1_WS_ARGS);
+  else k_p1tet_ws<false, true><<<grid, 512, WsSmem<false>::bytes, ctx->stream>>>(P1_WS_ARGS);
 #undef P1_WS_ARGS
   return NSGPU_OK;
 }

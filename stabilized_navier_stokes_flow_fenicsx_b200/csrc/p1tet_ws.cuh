@@ -24,8 +24,8 @@ constexpr int WS_SS = 120;         // incidence columns of a staging buffer: til
 constexpr int WS_VCAP = 96;        // distinct mesh vertices per tile (= bound on the total neighbour slots of a tile)
 constexpr int WS_NBUF = 3;
 #ifndef WS_REG_COMPUTE
-#define WS_REG_COMPUTE 208           // registers per thread of the compute warpgroups after setmaxnreg ...
-#define WS_REG_GATHER 88             // ... and of the helper warpgroup: 2 * 208 + 88 = 3 * 168 (the launch allocation of 384 threads)
+#define WS_REG_COMPUTE 208           // registers per thread of the two compute warpgroups after setmaxnreg ...
+#define WS_REG_GATHER 48             // ... and of the two gather warpgroups: 2 * 208 + 2 * 48 = 4 * 128 (the launch allocation of 512 threads)
 #endif
 constexpr int WS_CBLOB = 8 * WS_VCAP + 512 + 512 + 16;                                   // bytes per tile
 constexpr int WS_LIST = 8;          // gather-list entries held in the slot record itself (longer lists continue in the overflow area)
@@ -289,11 +289,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // named barriers: FULL[b] = 1 + b, EMPTY[b] = 4 + b (256 threads: one compute group + the gather group), compute group g: 7 + g, gather group: 9
 struct WsView { double2* stageJ; double4* stageF; };
 
-// phase B of one tile by the 128 threads of the gather warpgroup.  One warp of the group runs alone on its SM sub-partition
-// next to two algebra warps, so its own latencies are not hidden by other gather warps: every work item is written as
-// straight-line code -- record and list arrive with two independent loads, then all block pieces of the item are requested
-// (predicated by the list length) before the first add.  Items: off-diagonal slot groups (eight consecutive slots x four rows)
-// and vertices (diagonal block + residual: four rows x eight incidence lanes), dealt round-robin to the four warps.
+// phase B of one tile by the 128 threads of a gather warpgroup (48 registers per thread: plain loops; the two gather
+// groups of a CTA work on alternate tiles, so each SM sub-partition has two gather warps to hide each other's latencies).
+// Items: off-diagonal slot groups (eight consecutive slots x four rows, lane = 8 * row + slot) and vertices (diagonal block
+// + residual: four rows x eight incidence lanes), dealt round-robin to the four warps.
 template <bool WANT_J, bool WANT_F>
 __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, const double2* __restrict__ stageJ, const double4* __restrict__ stageF,
                                           const int tid, double* __restrict__ vals, double* __restrict__ F, const bool wide) {
@@ -306,64 +305,36 @@ __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, c
   const double2* base = stageJ + 2 * r * WS_SS;
   for (int item = warp; item < n_grp + nent; item += 4) {
     if (item < n_grp) {
-      // ---- eight consecutive off-diagonal slots: lane = 8 * row + slot; the two pieces of the lane's row over the slot's blocks.
-      // All loads of a batch of four list positions are issued before the first add (positions past the end of the list
-      // re-read the first block and are not added): the latency is paid once per batch, not once per block.
       const int j = 8 * item + (lane & 7);
-      const bool live = j < n_off;
-      const unsigned char* rec = H + 32 + 16 * nent + 32 * (live ? j : 0);
-      const int4 sr = *reinterpret_cast<const int4*>(rec);           // len | ovf << 16, out_off, rowlen
-      const uint4 li = *reinterpret_cast<const uint4*>(rec + 16);     // eight staging indices
-      const int len = live ? (sr.x & 0xffff) : 0;
-      double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
-      {
-        const uint32_t i0 = li.x & 0xffff, i1 = 1 < len ? li.x >> 16 : i0, i2 = 2 < len ? li.y & 0xffff : i0, i3 = 3 < len ? li.y >> 16 : i0;
-        const double2 a0 = base[i0], b0 = base[i0 + WS_SS], a1 = base[i1], b1 = base[i1 + WS_SS];
-        const double2 a2 = base[i2], b2 = base[i2 + WS_SS], a3 = base[i3], b3 = base[i3 + WS_SS];
-        const double m0 = 0 < len ? 1.0 : 0.0, m1 = 1 < len ? 1.0 : 0.0, m2 = 2 < len ? 1.0 : 0.0, m3 = 3 < len ? 1.0 : 0.0;
-        acc.x = (m0 * a0.x + m1 * a1.x) + (m2 * a2.x + m3 * a3.x); acc.y = (m0 * a0.y + m1 * a1.y) + (m2 * a2.y + m3 * a3.y);
-        acc.z = (m0 * b0.x + m1 * b1.x) + (m2 * b2.x + m3 * b3.x); acc.w = (m0 * b0.y + m1 * b1.y) + (m2 * b2.y + m3 * b3.y);
-      }
-      if (__any_sync(0xffffffffu, len > 4)) {
-        const uint32_t i0 = li.x & 0xffff;
-        const uint32_t i4 = 4 < len ? li.z & 0xffff : i0, i5 = 5 < len ? li.z >> 16 : i0, i6 = 6 < len ? li.w & 0xffff : i0, i7 = 7 < len ? li.w >> 16 : i0;
-        const double2 a4 = base[i4], b4 = base[i4 + WS_SS], a5 = base[i5], b5 = base[i5 + WS_SS];
-        const double2 a6 = base[i6], b6 = base[i6 + WS_SS], a7 = base[i7], b7 = base[i7 + WS_SS];
-        const double m4 = 4 < len ? 1.0 : 0.0, m5 = 5 < len ? 1.0 : 0.0, m6 = 6 < len ? 1.0 : 0.0, m7 = 7 < len ? 1.0 : 0.0;
-        acc.x += (m4 * a4.x + m5 * a5.x) + (m6 * a6.x + m7 * a7.x); acc.y += (m4 * a4.y + m5 * a5.y) + (m6 * a6.y + m7 * a7.y);
-        acc.z += (m4 * b4.x + m5 * b5.x) + (m6 * b6.x + m7 * b7.x); acc.w += (m4 * b4.y + m5 * b5.y) + (m6 * b6.y + m7 * b7.y);
-      }
-      if (len > WS_LIST) {   // rare: an edge shared by more than eight cells
-        const uint16_t* ov = reinterpret_cast<const uint16_t*>(H + 32 + 16 * nent + 32 * n_off) + ((unsigned)sr.x >> 16);
-        for (int q = WS_LIST; q < len; ++q) {
-          const double2 a0 = base[ov[q - WS_LIST]], a1 = base[ov[q - WS_LIST] + WS_SS];
+      if (j < n_off) {
+        const unsigned char* rec = H + 32 + 16 * nent + 32 * j;
+        const int4 sr = *reinterpret_cast<const int4*>(rec);           // len | ovf << 16, out_off, rowlen
+        const uint16_t* lst = reinterpret_cast<const uint16_t*>(rec + 16);
+        const int len = sr.x & 0xffff, n0 = len < WS_LIST ? len : WS_LIST;
+        double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll 2
+        for (int q = 0; q < n0; ++q) {
+          const double2 a0 = base[lst[q]], a1 = base[lst[q] + WS_SS];
           acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
         }
+        if (len > WS_LIST) {   // rare: an edge shared by more than eight cells
+          const uint16_t* ov = reinterpret_cast<const uint16_t*>(H + 32 + 16 * nent + 32 * n_off) + ((unsigned)sr.x >> 16);
+          for (int q = WS_LIST; q < len; ++q) {
+            const double2 a0 = base[ov[q - WS_LIST]], a1 = base[ov[q - WS_LIST] + WS_SS];
+            acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+          }
+        }
+        store_piece(vals + vbase + (uint32_t)sr.y + (int64_t)r * (uint32_t)sr.z, acc, wide);
       }
-      if (live) store_piece(vals + vbase + (uint32_t)sr.y + (int64_t)r * (uint32_t)sr.z, acc, wide);
     } else {
-      // ---- one vertex: diagonal block (block 0 of each of its incidences) and residual; lane = 8 * row + part
       const int le = item - n_grp, part = lane & 7;
       const int4 vr = *reinterpret_cast<const int4*>(H + 32 + 16 * le);
       const int ib = vr.x & 0xffff, ie = (unsigned)vr.x >> 16;
       const double* sf = reinterpret_cast<const double*>(stageF);
       double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
       double accF = 0.0;
-      {
-        // four load rounds of eight consecutive incidences, all requested before the first add (rounds past the end
-        // re-read the vertex's first incidence with weight zero)
-        const int i0 = ib + part < ie ? ib + part : ib, i1 = ib + part + 8 < ie ? ib + part + 8 : ib;
-        const int i2 = ib + part + 16 < ie ? ib + part + 16 : ib, i3 = ib + part + 24 < ie ? ib + part + 24 : ib;
-        const double m0 = ib + part < ie ? 1.0 : 0.0, m1 = ib + part + 8 < ie ? 1.0 : 0.0, m2 = ib + part + 16 < ie ? 1.0 : 0.0, m3 = ib + part + 24 < ie ? 1.0 : 0.0;
-        if (WANT_J) {
-          const double2 a0 = base[i0], b0 = base[WS_SS + i0], a1 = base[i1], b1 = base[WS_SS + i1];
-          const double2 a2 = base[i2], b2 = base[WS_SS + i2], a3 = base[i3], b3 = base[WS_SS + i3];
-          acc.x = (m0 * a0.x + m1 * a1.x) + (m2 * a2.x + m3 * a3.x); acc.y = (m0 * a0.y + m1 * a1.y) + (m2 * a2.y + m3 * a3.y);
-          acc.z = (m0 * b0.x + m1 * b1.x) + (m2 * b2.x + m3 * b3.x); acc.w = (m0 * b0.y + m1 * b1.y) + (m2 * b2.y + m3 * b3.y);
-        }
-        if (WANT_F) accF = (m0 * sf[4 * i0 + r] + m1 * sf[4 * i1 + r]) + (m2 * sf[4 * i2 + r] + m3 * sf[4 * i3 + r]);
-      }
-      for (int i = ib + part + 32; i < ie; i += 8) {   // more than 32 incidences at one vertex
+#pragma unroll 2
+      for (int i = ib + part; i < ie; i += 8) {
         if (WANT_J) {
           const double2 a0 = base[i], a1 = base[WS_SS + i];
           acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
@@ -387,13 +358,13 @@ __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, c
 }
 
 template <bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* __restrict__ wv, const uint8_t* __restrict__ bc_marker,
            const double* __restrict__ bc_value, const uint8_t* __restrict__ cblob, const uint8_t* __restrict__ hblob, const uint64_t* __restrict__ hword,
            double* __restrict__ vals, double* __restrict__ F, const int64_t n_tiles, const int64_t tile0, const bool wide) {
   using S = WsSmem<WANT_J>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int wg = threadIdx.x >> 7;         // 0, 1: compute warpgroups; 2: helper (loads + gather)
+  const int wg = threadIdx.x >> 7;         // 0, 1: compute warpgroups; 2, 3: gather warpgroups
   const int tid = threadIdx.x & 127;
   const int nk = (int)((n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA: tile0 + blockIdx.x + k * gridDim.x
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::off_bar);                   // TAB[3], RING[2][2]
@@ -403,20 +374,40 @@ k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* _
   }
   __syncthreads();
   auto stage_of = [&](int b) { return smem_raw + (size_t)b * S::stage; };
-  auto ring_of = [&](int g, int m) { return smem_raw + S::off_ring + (size_t)(2 * g + (m & 1)) * WS_CBLOB; };   // C blob of group g's local iteration m
-  // named barriers (256 threads = one compute group + the helper group): FULL[b] = 1 + b, EMPTY[b] = 4 + b (staging buffer b),
-  // TFULL[g] = 7 + g (group g's vertex table is filled), TFREE[g] = 9 + g (group g has read its inputs); 11: helper group only
   if (wg < 2) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
-    // ---------------------------------------------------------------- compute warpgroup g: tiles k = g, g + 2, ...
     const int g = wg;
-    const double2* tab = reinterpret_cast<const double2*>(smem_raw + S::off_vtab + (size_t)g * S::vtab);
+    const int nm = nk > g ? (nk - g + 1) / 2 : 0;                                       // this group's tiles: k = g + 2 m
+    unsigned char* ring = smem_raw + S::off_ring + (size_t)g * 2 * WS_CBLOB;
+    double2* tab = reinterpret_cast<double2*>(smem_raw + S::off_vtab + (size_t)g * S::vtab);
     uint64_t* rbar = bars + 3 + 2 * g;
-    for (int k = g, m = 0; k < nk; k += 2, ++m) {
-      const int b = k % 3;
-      named_bar_sync(7 + g, 256);              // TFULL: coordinates + state of this tile's vertices are in the table
-      mbar_wait(rbar + (m & 1), (m >> 1) & 1);  // the tile's C blob (landed long ago)
-      const unsigned char* rs = ring_of(g, m);
+    auto fetch_ring = [&](const int m) {   // one thread: C blob of local iteration m -> ring slot m & 1
+      const int64_t t = tile0 + (int64_t)blockIdx.x + (int64_t)(g + 2 * m) * gridDim.x;
+      mbar_expect_tx(rbar + (m & 1), WS_CBLOB);
+      bulk_g2s(ring + (m & 1) * WS_CBLOB, cblob + t * WS_CBLOB, WS_CBLOB, rbar + (m & 1));
+    };
+    auto fetch_table = [&](const int m) {  // coordinates + state of the distinct vertices of iteration m (its C blob is in the ring)
+      const unsigned char* rs = ring + (m & 1) * WS_CBLOB;
+      const int n = *reinterpret_cast<const int*>(rs + 8 * WS_VCAP + 1024) * PIPE_VREC;
+      const int2* vl = reinterpret_cast<const int2*>(rs);
+      for (int item = tid; item < n; item += 128) {
+        const int i = item / PIPE_VREC, c = item - i * PIPE_VREC;
+        const int2 e = vl[i];
+        if (c < 3) cp_async8(reinterpret_cast<double*>(tab + i * PIPE_VREC) + c, xg + 3 * (int64_t)e.x + c);
+        else cp_async16_ca(tab + i * PIPE_VREC + (c - 1), wv + e.y + 2 * (c - 3));
+      }
+    };
+    if (nm > 0) {
+      if (tid == 0) { fetch_ring(0); if (nm > 1) fetch_ring(1); }
+      mbar_wait(rbar, 0);
+      fetch_table(0);
+    }
+    cp_async_commit();
+    for (int m = 0; m < nm; ++m) {
+      const int k = g + 2 * m, b = k % 3;
+      cp_async_wait_all();
+      named_bar_sync(7 + g, 128);            // the vertex table of this tile is complete and visible
+      const unsigned char* rs = ring + (m & 1) * WS_CBLOB;
       const uint32_t loc = reinterpret_cast<const uint32_t*>(rs + 8 * WS_VCAP)[tid];
       const uint32_t cm = reinterpret_cast<const uint32_t*>(rs + 8 * WS_VCAP + 512)[tid];
       const int ninc = reinterpret_cast<const int*>(rs + 8 * WS_VCAP + 1024)[1];
@@ -431,9 +422,15 @@ k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* _
         u[a][0] = q2.x; u[a][1] = q2.y; u[a][2] = q3.x; p[a] = q3.y;
         if (cm & INC_BC_BIT) lead[a] = reinterpret_cast<const int2*>(rs)[i].y;   // first dofs are only needed by the Dirichlet path
       }
-      if (k + 2 < nk) named_bar_arrive(9 + g, 256);   // TFREE: table and ring slot may be refilled for the group's next tiles
+      named_bar_sync(7 + g, 128);            // table and ring slot are consumed: refill them for the group's next tiles
+      if (m + 1 < nm) {
+        mbar_wait(rbar + ((m + 1) & 1), ((m + 1) >> 1) & 1);
+        fetch_table(m + 1);
+      }
+      cp_async_commit();
+      if (tid == 0 && m + 2 < nm) fetch_ring(m + 2);
       const WsView v{reinterpret_cast<double2*>(stage_of(b)), reinterpret_cast<double4*>(stage_of(b) + (WANT_J ? (size_t)32 * WS_SS * sizeof(double2) : 0))};
-      auto wait_empty = [&]() { if (k >= WS_NBUF) named_bar_sync(4 + b, 256); };   // the helper is done with tile k - 3
+      auto wait_empty = [&]() { if (k >= WS_NBUF) named_bar_sync(4 + b, 256); };   // the gather group is done with tile k - 3
       const int col = tid < WS_SS ? tid : tid - 8;
       if ((tid & ~31) < ninc)
         phase_a_core<WS_SS, WANT_J, WANT_F>(v, col, lead, cm, x, u, p, form, xg, wv, nullptr, true, bc_marker, bc_value, wait_empty);
@@ -444,72 +441,35 @@ k_p1tet_ws(const FormParams form, const double* __restrict__ xg, const double* _
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_GATHER));
-    // ---------------------------------------------------------------- helper warpgroup: every load of the CTA, and the gather
+    // ---------------------------------------------------------------- gather warpgroup h: tiles j = h, h + 2, ... (parked by compute group h)
+    const int h = wg - 2;
     unsigned char* htab = smem_raw + S::off_htab;
-    auto tile_of = [&](const int k) { return tile0 + (int64_t)blockIdx.x + (int64_t)k * gridDim.x; };
+    auto word_of = [&](const int k) { return hword[tile0 + (int64_t)blockIdx.x + (int64_t)k * gridDim.x]; };
     auto fetch_h = [&](const int k, const uint64_t w) {   // one thread: H blob of tile k -> table buffer k % 3
       const int b = k % WS_NBUF;
       const uint32_t bytes = (uint32_t)(w & 0xffff) << 4;
       mbar_expect_tx(bars + b, bytes);
       bulk_g2s(htab + (size_t)b * WS_HMAX, hblob + ((w >> 16) << 4), bytes, bars + b);
     };
-    auto fetch_ring = [&](const int k) {                   // one thread: C blob of tile k -> its group's ring slot
-      const int g = k & 1, m = k >> 1;
-      uint64_t* rb = bars + 3 + 2 * g + (m & 1);
-      mbar_expect_tx(rb, WS_CBLOB);
-      bulk_g2s(ring_of(g, m), cblob + tile_of(k) * WS_CBLOB, WS_CBLOB, rb);
-    };
-    auto fetch_table = [&](const int k) {                  // all threads: coordinates + state of the distinct vertices of tile k
-      const int g = k & 1, m = k >> 1;
-      mbar_wait(bars + 3 + 2 * g + (m & 1), (m >> 1) & 1);   // its C blob (vertex list)
-      const unsigned char* rs = ring_of(g, m);
-      double2* tab = reinterpret_cast<double2*>(smem_raw + S::off_vtab + (size_t)g * S::vtab);
-      const int n = *reinterpret_cast<const int*>(rs + 8 * WS_VCAP + 1024) * PIPE_VREC;
-      const int2* vl = reinterpret_cast<const int2*>(rs);
-      for (int item = tid; item < n; item += 128) {
-        const int i = item / PIPE_VREC, c = item - i * PIPE_VREC;
-        const int2 e = vl[i];
-        if (c < 3) cp_async8(reinterpret_cast<double*>(tab + i * PIPE_VREC) + c, xg + 3 * (int64_t)e.x + c);
-        else cp_async16_ca(tab + i * PIPE_VREC + (c - 1), wv + e.y + 2 * (c - 3));
-      }
-    };
-    uint64_t wnext = 0;
+    uint64_t wnext = 0;                       // packed offset / size of the H blob this group's elected thread requests next (tile j + 3)
     if (tid == 0) {
-      for (int k = 0; k < nk && k < WS_NBUF; ++k) fetch_h(k, hword[tile_of(k)]);
-      if (nk > WS_NBUF) wnext = hword[tile_of(WS_NBUF)];
-      for (int k = 0; k < nk && k < 4; ++k) fetch_ring(k);
+      if (h == 0) for (int k = 0; k < nk && k < WS_NBUF; ++k) fetch_h(k, word_of(k));
+      if (h + WS_NBUF < nk) wnext = word_of(h + WS_NBUF);
     }
-    for (int k = 0; k < nk && k < 2; ++k) fetch_table(k);
-    cp_async_commit();
-    cp_async_wait_all();
-    if (nk > 0) named_bar_arrive(7, 256);
-    if (nk > 1) named_bar_arrive(8, 256);
-    for (int j = -2; j < nk; ++j) {
-      if (j >= 0) {
-        const int b = j % WS_NBUF;
-        mbar_wait(bars + b, (j / WS_NBUF) & 1);
-        named_bar_sync(1 + b, 256);            // FULL[b]: the row slabs of tile j are parked
-        const unsigned char* st = stage_of(b);
-        ws_gather<WANT_J, WANT_F>(htab + (size_t)b * WS_HMAX, reinterpret_cast<const double2*>(st),
-                                  reinterpret_cast<const double4*>(st + (WANT_J ? (size_t)32 * WS_SS * sizeof(double2) : 0)), tid, vals, F, wide);
-        if (j + WS_NBUF < nk) {
-          named_bar_sync(11, 128);             // every helper thread is done with staging buffer and table b
-          named_bar_arrive(4 + b, 256);        // EMPTY[b]
-          if (tid == 0) {
-            fetch_h(j + WS_NBUF, wnext);
-            if (j + WS_NBUF + 1 < nk) wnext = hword[tile_of(j + WS_NBUF + 1)];
-          }
+    for (int j = h; j < nk; j += 2) {
+      const int b = j % WS_NBUF;
+      mbar_wait(bars + b, (j / WS_NBUF) & 1);
+      named_bar_sync(1 + b, 256);            // FULL[b]: the row slabs of tile j are parked
+      const unsigned char* st = stage_of(b);
+      ws_gather<WANT_J, WANT_F>(htab + (size_t)b * WS_HMAX, reinterpret_cast<const double2*>(st),
+                                reinterpret_cast<const double4*>(st + (WANT_J ? (size_t)32 * WS_SS * sizeof(double2) : 0)), tid, vals, F, wide);
+      if (j + WS_NBUF < nk) {
+        named_bar_sync(9 + h, 128);          // every thread of this gather group is done with staging buffer and table b
+        named_bar_arrive(4 + b, 256);        // EMPTY[b]: compute group (j + 3) % 2 may park tile j + 3 there
+        if (tid == 0) {
+          fetch_h(j + WS_NBUF, wnext);       // ... and the other gather group finds its table in buffer b
+          if (j + 2 + WS_NBUF < nk) wnext = word_of(j + 2 + WS_NBUF);
         }
-      }
-      if (j >= -1 && j + 3 < nk) {             // the vertex table requested one round ago (tile j + 3) has had a whole gather to land
-        cp_async_wait_all();
-        named_bar_arrive(7 + ((j + 3) & 1), 256);   // TFULL
-      }
-      if (j + 4 < nk) {
-        named_bar_sync(9 + (j & 1), 256);      // TFREE: the group of tile j + 4 has read the inputs of its tile j + 2
-        if (tid == 0 && j + 6 < nk) fetch_ring(j + 6);
-        fetch_table(j + 4);
-        cp_async_commit();
       }
     }
   }

@@ -9,6 +9,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _permuted(part, seed):
+    """The same partition behind a numbering in which the dofs of a vertex are scattered (owned dofs permuted among the owned,
+    ghosts among the ghosts), like W.dofmap.list of the reference's mixed space after dolfinx's reordering."""
+    import copy
+    rng = np.random.default_rng(seed)
+    n_owned, n_ghost = part.n_owned, part.n_ghost
+    perm = np.concatenate([rng.permutation(n_owned), n_owned + rng.permutation(n_ghost)]).astype(np.int64)   # old local -> new local
+    p = copy.copy(part)
+    p.dofmap = perm[part.dofmap].astype(np.int32)
+    l2g = np.empty_like(part.local_to_global); l2g[perm] = part.local_to_global
+    p.local_to_global = l2g
+    p.ghost_global = l2g[n_owned:]
+    go = np.empty_like(part.ghost_owner); go[perm[n_owned:] - n_owned] = part.ghost_owner
+    p.ghost_owner = go
+    w = np.empty_like(part.w); w[perm] = part.w
+    p.w = w
+    p.bcs = [(perm[np.asarray(d)].astype(np.int32), v) for d, v in part.bcs]
+    return p
+
+
 def main():
     from oracle import oracle
     from stabilized_navier_stokes_flow_fenicsx_b200 import distributed as D
@@ -17,13 +37,17 @@ def main():
     n_cross, n_long = 6, 20
     comm = D.Comm.from_env()
     rank, size = comm.rank, comm.size
-    part = D.duct_partition(n_cross, n_long, rank, size)
-    for kernel in (0, 1):
+    part0 = D.duct_partition(n_cross, n_long, rank, size)
+    # (kernel, overlap, permuted): auto kernel with the overlapped exchanges, the same with serial exchanges, the generic
+    # kernel, and the auto kernel behind a dolfinx-like numbering (dofs of a vertex scattered: the library renumbers internally)
+    for kernel, overlap, permuted in ((0, 1, False), (0, 0, False), (1, 1, False), (0, 1, True)):
+        part = _permuted(part0, 100 + rank) if permuted else part0
         asm = NSAssembler(part.x, part.cells, part.dofmap, vdeg=1, n_dofs_owned=part.n_owned, n_dofs_ghost=part.n_ghost,
                           n_cells_owned=part.n_cells_owned, device=int(os.environ.get("LOCAL_RANK", 0)))
         asm.set_form(flavour=0, nu=0.1)
         asm.set_bcs(part.bcs)
         asm.set_option("kernel", kernel)
+        asm.set_option("overlap", overlap)
         D.attach(asm, part, comm)
         plans = D.finish_pattern_exchange(asm, part, comm)
         n_owned, n_dofs = part.n_owned, part.n_owned + part.n_ghost
@@ -69,7 +93,13 @@ def main():
         xs, info = asm.tfqmr(F[:n_owned], rtol=1e-12, max_it=4000, pc=4)
         ex = np.abs(xs - x_ref[l2g[:n_owned]]).max()
         assert ex <= 1e-8 * np.abs(x_ref).max(), f"rank {rank} kernel {kernel}: TFQMR err {ex} {info}"
-        print(f"rank {rank}/{size} kernel {kernel}: J {worst:.2e} F {eF:.2e} Jx {ey:.2e} tfqmr {ex:.2e} in {info['its']} its "
+        asm.set_option("stream_host", 0)
+        asm.jacobian_residual(xin)
+        kname = asm.last_kernel_name()
+        if kernel == 0:
+            assert kname == "p1tet_ws" and asm.last_spmv_name() == "spmv_block4", (kname, asm.last_spmv_name())
+        print(f"rank {rank}/{size} kernel {kernel} ({kname}, {asm.last_spmv_name()}) overlap {overlap} permuted {int(permuted)}: "
+              f"J {worst:.2e} F {eF:.2e} Jx {ey:.2e} tfqmr {ex:.2e} in {info['its']} its "
               f"(n_owned {n_owned}, ghosts {part.n_ghost}, col ghosts {asm.n_cols - n_dofs})", flush=True)
         asm.close()
     comm.close()
