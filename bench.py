@@ -177,6 +177,8 @@ def run_ours(args):
         asm.set_option("ws", args.ws)
     if os.environ.get("NSGPU_OVERLAP") is not None:                 # experiment switch: 0 = serial exchanges after the kernel
         asm.set_option("overlap", int(os.environ["NSGPU_OVERLAP"]))
+    if os.environ.get("NSGPU_SM_RESERVE") is not None:
+        asm.set_option("sm_reserve", int(os.environ["NSGPU_SM_RESERVE"]))
     if args.pipe is not None:
         asm.set_option("pipe", args.pipe)
     D.attach(asm, part, comm)                                       # the library's own NCCL communicator

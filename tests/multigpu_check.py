@@ -9,24 +9,38 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def _permuted(part, seed):
-    """The same partition behind a numbering in which the dofs of a vertex are scattered (owned dofs permuted among the owned,
-    ghosts among the ghosts), like W.dofmap.list of the reference's mixed space after dolfinx's reordering."""
-    import copy
+def _local_perm(n_owned, n_ghost, seed):
     rng = np.random.default_rng(seed)
+    return np.concatenate([rng.permutation(n_owned), n_owned + rng.permutation(n_ghost)]).astype(np.int64)   # old local -> new local
+
+
+def _permuted(part, parts_of_all_ranks):
+    """The same partition behind a dolfinx-like numbering in which the dofs of a vertex are scattered: on every rank the owned
+    dofs are permuted among the owned and the ghosts among the ghosts, and -- as in a dolfinx index map -- the GLOBAL index of
+    an owned dof is (the rank's offset + its local index), so the global numbering changes with it.  Returns the new
+    partition and, per new local dof, its global index in the ORIGINAL numbering (for the comparison with the serial oracle)."""
+    import copy
+    new_global = {}
+    for q, pq in enumerate(parts_of_all_ranks):                     # every rank can reproduce every rank's permutation
+        perm_q = _local_perm(pq.n_owned, pq.n_ghost, 100 + q)
+        new_global[q] = (pq.local_to_global[: pq.n_owned], pq.global_offset + perm_q[: pq.n_owned])
+    n_total = sum(len(v[0]) for v in new_global.values())
+    old2new = np.empty(n_total, dtype=np.int64)
+    for og, ng in new_global.values():
+        old2new[og] = ng
     n_owned, n_ghost = part.n_owned, part.n_ghost
-    perm = np.concatenate([rng.permutation(n_owned), n_owned + rng.permutation(n_ghost)]).astype(np.int64)   # old local -> new local
+    perm = _local_perm(n_owned, n_ghost, 100 + part.rank)
     p = copy.copy(part)
     p.dofmap = perm[part.dofmap].astype(np.int32)
-    l2g = np.empty_like(part.local_to_global); l2g[perm] = part.local_to_global
-    p.local_to_global = l2g
-    p.ghost_global = l2g[n_owned:]
+    l2g_old = np.empty_like(part.local_to_global); l2g_old[perm] = part.local_to_global
+    p.local_to_global = old2new[l2g_old]
+    p.ghost_global = p.local_to_global[n_owned:]
     go = np.empty_like(part.ghost_owner); go[perm[n_owned:] - n_owned] = part.ghost_owner
     p.ghost_owner = go
     w = np.empty_like(part.w); w[perm] = part.w
     p.w = w
     p.bcs = [(perm[np.asarray(d)].astype(np.int32), v) for d, v in part.bcs]
-    return p
+    return p, l2g_old, old2new
 
 
 def main():
@@ -41,7 +55,10 @@ def main():
     # (kernel, overlap, permuted): auto kernel with the overlapped exchanges, the same with serial exchanges, the generic
     # kernel, and the auto kernel behind a dolfinx-like numbering (dofs of a vertex scattered: the library renumbers internally)
     for kernel, overlap, permuted in ((0, 1, False), (0, 0, False), (1, 1, False), (0, 1, True)):
-        part = _permuted(part0, 100 + rank) if permuted else part0
+        if permuted:
+            part, l2g_ser, old2new = _permuted(part0, [D.duct_partition(n_cross, n_long, q, size) for q in range(size)])
+        else:
+            part, l2g_ser, old2new = part0, part0.local_to_global, None
         asm = NSAssembler(part.x, part.cells, part.dofmap, vdeg=1, n_dofs_owned=part.n_owned, n_dofs_ghost=part.n_ghost,
                           n_cells_owned=part.n_cells_owned, device=int(os.environ.get("LOCAL_RANK", 0)))
         asm.set_form(flavour=0, nu=0.1)
@@ -62,8 +79,13 @@ def main():
         oracle.set_bc(gF, [b[0] for b in bcs], [b[1] for b in bcs], w)
         import scipy.sparse as sps
         A = sps.csr_matrix((gv, gi, gp), shape=(sp.n_dofs,) * 2)
-        l2g = part.local_to_global
-        colg = np.concatenate([l2g, plans.col_ghost_global]) if plans is not None else l2g
+        l2g = l2g_ser                                                # local dof -> global dof of the serial oracle
+        colg_new = np.concatenate([part.local_to_global, plans.col_ghost_global]) if plans is not None else part.local_to_global
+        if old2new is None:
+            colg = colg_new
+        else:                                                        # column ghosts arrive in the renumbered global numbering
+            new2old = np.empty_like(old2new); new2old[old2new] = np.arange(len(old2new))
+            colg = new2old[colg_new]
         # ghosts deliberately wrong on input: the forward halo must refresh them
         xin = part.w.copy()
         xin[n_owned:] = 1e30
