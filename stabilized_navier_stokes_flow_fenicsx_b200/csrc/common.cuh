@@ -200,6 +200,8 @@ int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out);
 void krylov_free(nsgpu_ctx* ctx);
 // renumber.cu
 int renumber_build(nsgpu_ctx* ctx);
+int renumber_extend_cols(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_local, const int32_t* slot, const int32_t* size,
+                         std::vector<int32_t>& o_leader, std::vector<int32_t>& o_slot, std::vector<int32_t>& o_size);
 void renumber_free(nsgpu_ctx* ctx);
 int perm_in(nsgpu_ctx* ctx, const double* d_src_caller, double* d_dst_internal, int64_t n_perm, int64_t n_tot);
 int perm_out(nsgpu_ctx* ctx, const double* d_src_internal, double* d_dst_caller, int64_t n_perm, int64_t n_tot);

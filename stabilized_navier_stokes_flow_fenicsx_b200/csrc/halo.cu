@@ -251,8 +251,8 @@ extern "C" int nsgpu_set_halo(nsgpu_ctx* ctx, int n_neigh, const int32_t* neigh_
   for (int64_t k = 0; k < ns; ++k) NS_REQUIRE(ctx, si[k] >= 0 && si[k] < ctx->n_cols, "set_halo: send index out of range");
   for (int64_t k = 0; k < nr; ++k) NS_REQUIRE(ctx, ri[k] >= 0 && ri[k] < ctx->n_cols, "set_halo: receive index out of range");
   if (ctx->d_perm) {
-    for (auto& d : si) if (d < ctx->n_dofs) d = ctx->h_perm[d];
-    for (auto& d : ri) if (d < ctx->n_dofs) d = ctx->h_perm[d];
+    for (auto& d : si) d = ctx->h_perm[d];
+    for (auto& d : ri) d = ctx->h_perm[d];
   }
   if (ns) NS_CUDA(ctx, h2d_sync(ctx, h.d_send_idx, si.data(), sizeof(int32_t) * ns));
   if (nr) NS_CUDA(ctx, h2d_sync(ctx, h.d_recv_idx, ri.data(), sizeof(int32_t) * nr));

@@ -277,7 +277,7 @@ int nsgpu_add_pattern_entries(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, co
   if (permuted(ctx))
     for (int64_t k = 0; k < n; ++k) {
       ctx->extra_rows[at + k] = ctx->h_perm[rows[k]];
-      if (cols[k] < ctx->n_dofs) ctx->extra_cols[at + k] = ctx->h_perm[cols[k]];
+      ctx->extra_cols[at + k] = ctx->h_perm[cols[k]];
     }
   ctx->pattern_built = false;
   return NSGPU_OK;
@@ -294,11 +294,10 @@ int nsgpu_set_col_ghosts(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_
   }
   ctx->n_cols = ctx->n_dofs + n_extra;
   cudaFree(ctx->d_x_last); ctx->d_x_last = nullptr; ctx->jac_valid = false;
-  ctx->colx_leader.assign(leader_local, leader_local + n_extra);
-  ctx->colx_slot.assign(slot, slot + n_extra);
-  ctx->colx_size.assign(size, size + n_extra);
   ctx->pattern_built = false;
   int rc;
+  // entity tables in the internal numbering (column ghosts grouped by vertex when the library renumbers, renumber.cu)
+  if ((rc = renumber_extend_cols(ctx, n_extra, leader_local, slot, size, ctx->colx_leader, ctx->colx_slot, ctx->colx_size))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_xvec, ctx->n_cols))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_y, ctx->n_cols))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_F, ctx->n_cols))) return rc;
@@ -413,9 +412,9 @@ int nsgpu_jacobian_residual_dev(nsgpu_ctx* ctx, double* x_local_dev, int want_ja
     return rc;
   }
   // caller-ordered device vectors: one gather pass in, one out
-  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_cols, ctx->n_cols))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
-  if (ctx->nranks > 1 && (rc = perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_dofs, ctx->n_cols))) return rc;   // the refreshed ghost entries
+  if (ctx->nranks > 1 && (rc = perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_cols, ctx->n_cols))) return rc;   // the refreshed ghost entries
   if ((rc = assemble_impl(ctx, ctx->d_xvec, want_jacobian != 0, F_local_dev != nullptr, ctx->d_F))) return rc;
   if (F_local_dev) {
     if (ctx->check_finite && (rc = check_finite_impl(ctx, ctx->d_F, ctx->n_owned, "residual", false))) return rc;
@@ -505,7 +504,7 @@ int nsgpu_spmv_dev(nsgpu_ctx* ctx, double* x_local_dev, double* y_owned_dev) {
     if ((rc = halo_forward(ctx, x_local_dev))) return rc;
     return spmv_impl(ctx, x_local_dev, y_owned_dev);
   }
-  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_cols, ctx->n_cols))) return rc;
   if ((rc = halo_forward(ctx, ctx->d_xvec))) return rc;
   if ((rc = spmv_impl(ctx, ctx->d_xvec, ctx->d_y))) return rc;
   return perm_out(ctx, ctx->d_y, y_owned_dev, ctx->n_owned, ctx->n_owned);
@@ -536,9 +535,9 @@ int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_d
   int rc;
   if ((rc = perm_in(ctx, b_owned_dev, ctx->d_F, ctx->n_owned, ctx->n_owned))) return rc;
   if (zero_guess) NS_CUDA(ctx, cudaMemsetAsync(ctx->d_xvec, 0, sizeof(double) * ctx->n_cols, ctx->stream));
-  else if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_dofs, ctx->n_cols))) return rc;
+  else if ((rc = perm_in(ctx, x_local_dev, ctx->d_xvec, ctx->n_cols, ctx->n_cols))) return rc;
   if ((rc = tfqmr_impl(ctx, ctx->d_F, ctx->d_xvec, rtol, atol, max_it, pc, zero_guess != 0, its_out, rnorm_out, r0norm_out))) return rc;
-  return perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_dofs, ctx->n_cols);
+  return perm_out(ctx, ctx->d_xvec, x_local_dev, ctx->n_cols, ctx->n_cols);
 }
 
 int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double rtol, double atol, int max_it, int pc, int zero_guess,

@@ -200,6 +200,55 @@ int renumber_build(nsgpu_ctx* ctx) {
 #undef RN_CUDA
 }
 
+// Column ghosts (dofs of no local cell that appear in owned rows through other ranks' ghost rows, nsgpu_set_col_ghosts) arrive
+// in the caller's order -- with a dolfinx numbering the four dofs of such a vertex are scattered.  Internally they are grouped:
+// column ghost (entity rank e, slot s) -> n_dofs + 4 e + s, entities in the order of their first dof.  The permutation arrays are
+// extended to n_cols entries (identity when the ghosts are not complete 4-dof entities) and the entity tables are translated.
+int renumber_extend_cols(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_local, const int32_t* slot, const int32_t* size,
+                         std::vector<int32_t>& o_leader, std::vector<int32_t>& o_slot, std::vector<int32_t>& o_size) {
+  o_leader.assign(leader_local, leader_local + n_extra);
+  o_slot.assign(slot, slot + n_extra);
+  o_size.assign(size, size + n_extra);
+  if (!ctx->d_perm) return NSGPU_OK;
+  const int64_t n = ctx->n_dofs, nc = n + n_extra;
+  ctx->h_perm.resize((size_t)nc);
+  for (int64_t k = 0; k < n_extra; ++k) ctx->h_perm[(size_t)(n + k)] = (int32_t)(n + k);
+  // entity ranks in the order of the leaders; usable only if every entity is a complete vertex (slots 0..3 once each)
+  std::vector<int32_t> leaders(leader_local, leader_local + n_extra);
+  std::sort(leaders.begin(), leaders.end());
+  leaders.erase(std::unique(leaders.begin(), leaders.end()), leaders.end());
+  bool ok = n_extra % 4 == 0 && (int64_t)leaders.size() * 4 == n_extra;
+  std::vector<uint8_t> seen((size_t)n_extra, 0);
+  std::vector<int32_t> ext((size_t)n_extra, 0);
+  for (int64_t k = 0; k < n_extra && ok; ++k) {
+    const int64_t e = std::lower_bound(leaders.begin(), leaders.end(), leader_local[k]) - leaders.begin();
+    if (size[k] != 4 || slot[k] < 0 || slot[k] > 3) { ok = false; break; }
+    const int64_t pos = 4 * e + slot[k];
+    if (seen[(size_t)pos]) { ok = false; break; }
+    seen[(size_t)pos] = 1;
+    ext[(size_t)k] = (int32_t)(n + pos);
+  }
+  if (ok)
+    for (int64_t k = 0; k < n_extra; ++k) {
+      ctx->h_perm[(size_t)(n + k)] = ext[(size_t)k];
+      const int64_t pos = ext[(size_t)k] - n;
+      o_leader[(size_t)pos] = (int32_t)(n + 4 * (pos / 4));
+      o_slot[(size_t)pos] = (int32_t)(pos % 4);
+      o_size[(size_t)pos] = 4;
+    }
+  // device copies of the extended permutation and its inverse
+  std::vector<int32_t> h_iperm((size_t)nc);
+  int32_t *d_p = nullptr, *d_ip = nullptr;
+  NS_CUDA(ctx, cudaMalloc(&d_p, sizeof(int32_t) * (size_t)nc));
+  NS_CUDA(ctx, cudaMalloc(&d_ip, sizeof(int32_t) * (size_t)nc));
+  for (int64_t d = 0; d < nc; ++d) h_iperm[(size_t)ctx->h_perm[(size_t)d]] = (int32_t)d;
+  NS_CUDA(ctx, h2d_sync(ctx, d_p, ctx->h_perm.data(), sizeof(int32_t) * (size_t)nc));
+  NS_CUDA(ctx, h2d_sync(ctx, d_ip, h_iperm.data(), sizeof(int32_t) * (size_t)nc));
+  cudaFree(ctx->d_perm); cudaFree(ctx->d_iperm);
+  ctx->d_perm = d_p; ctx->d_iperm = d_ip;
+  return NSGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- vectors
 __global__ void k_perm_in(int64_t n, int64_t n_tot, const int32_t* __restrict__ iperm, const double* __restrict__ src, double* __restrict__ dst) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // internal index
@@ -309,7 +358,7 @@ int ensure_caller_pattern(nsgpu_ctx* ctx) {
   if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tb);
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_len, ctx->d_indptr_c, n + 1, s);
   if (e == cudaSuccess) {
-    k_cp_fill<<<(unsigned)ceil_div(n > 0 ? n : 1, 64), 64, 0, s>>>(n, ctx->n_dofs, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
+    k_cp_fill<<<(unsigned)ceil_div(n > 0 ? n : 1, 64), 64, 0, s>>>(n, ctx->n_cols, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
                                                                     ctx->d_indptr_c, ctx->d_indices_c);
     e = cudaStreamSynchronize(s);
   }
@@ -325,7 +374,7 @@ int ensure_caller_pattern(nsgpu_ctx* ctx) {
 int export_values(nsgpu_ctx* ctx, double* d_dst) {
   int rc = ensure_caller_pattern(ctx);
   if (rc) return rc;
-  k_cp_values<true><<<g256(ctx->n_rows * 8), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->n_dofs, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
+  k_cp_values<true><<<g256(ctx->n_rows * 8), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->n_cols, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
                                                                       ctx->d_indptr_c, ctx->d_indices_c, ctx->d_vals, d_dst);
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
@@ -335,7 +384,7 @@ int export_values(nsgpu_ctx* ctx, double* d_dst) {
 int import_values(nsgpu_ctx* ctx, double* d_src) {
   int rc = ensure_caller_pattern(ctx);
   if (rc) return rc;
-  k_cp_values<false><<<g256(ctx->n_rows * 8), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->n_dofs, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
+  k_cp_values<false><<<g256(ctx->n_rows * 8), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->n_cols, ctx->d_perm, ctx->d_iperm, ctx->d_indptr, ctx->d_indices,
                                                                        ctx->d_indptr_c, ctx->d_indices_c, ctx->d_vals, d_src);
   ctx->launches += 1;
   NS_CUDA(ctx, cudaGetLastError());
@@ -375,7 +424,7 @@ int translate_positions(nsgpu_ctx* ctx, int64_t n, const int64_t* h_pos_c, int64
   NS_CUDA(ctx, cudaMalloc(&d_pc, sizeof(int64_t) * n));
   cudaError_t e = cudaMemcpyAsync(d_pc, h_pos_c, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    k_cp_positions<<<g256(n), 256, 0, ctx->stream>>>(n, ctx->n_rows, ctx->n_dofs, ctx->d_perm, ctx->d_indptr, ctx->d_indices, ctx->d_indptr_c,
+    k_cp_positions<<<g256(n), 256, 0, ctx->stream>>>(n, ctx->n_rows, ctx->n_cols, ctx->d_perm, ctx->d_indptr, ctx->d_indices, ctx->d_indptr_c,
                                                     ctx->d_indices_c, d_pc, d_pos_i);
     e = cudaStreamSynchronize(ctx->stream);
   }
