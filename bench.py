@@ -35,10 +35,13 @@ NU, CI = 0.1, 36.0
 # Keyed by (workload, kernel name): the figures are only quoted when the run used that kernel on that workload on 1 GPU.
 NCU_PROFILE = {
     ("L", "p1tet_pipe"): {"traffic": 22.49e9, "flop_per_cell": 5426, "source": "profiles/r1c_ncu_full_L_p1tet_pipe.txt"},
+    # round 2, warp-specialised kernel: dram 8.12 GB read + 16.47 GB written (the per-tile blobs add ~2 GB of reads); executed
+    # fp64 thread instructions 2 * 104.92 G DFMA + 42.93 G DMUL + 38.44 G DADD (source page of the capture)
+    ("L", "p1tet_ws"): {"traffic": 24.58e9, "flop_per_cell": 5786, "source": "profiles/r2_ncu_full_L_p1tet_ws.txt"},
 }
 # executed fp64 work of the row-owner kernels per cell when no capture of the exact kernel is on file: 2*DFMA + DADD + DMUL thread
 # instructions, 4 incidences per cell (the algebra is the same code in every variant; DESIGN.md 4.3 derives the count)
-FLOP_PER_CELL_MODEL = 5426
+FLOP_PER_CELL_MODEL = 5786
 
 
 def peaks():

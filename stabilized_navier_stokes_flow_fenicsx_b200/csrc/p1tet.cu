@@ -649,9 +649,14 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
 #ifndef NS_NO_PARK
           sts2(stage_idx(CAP, 0, 0, tid), D[0][0], D[0][1]); sts2(stage_idx(CAP, 0, 1, tid), D[0][2], D[1][0]);
           sts2(stage_idx(CAP, 0, 2, tid), D[1][1], D[1][2]); sts2(stage_idx(CAP, 0, 3, tid), D[2][0], D[2][1]);
+#ifndef NS_PARK_D_ONLY
           sts2(stage_idx(CAP, 0, 4, tid), D[2][2], g[1][2]); sts2(stage_idx(CAP, 0, 5, tid), g[2][2], g[3][2]);
 #pragma unroll
           for (int n = 1; n < 4; ++n) sts2(stage_idx(CAP, n, 5, tid), g[n][0], g[n][1]);
+#else
+          sts2(stage_idx(CAP, 0, 4, tid), D[2][2], 0.0);
+          (void)g;
+#endif
 #endif
         }
         __device__ void get_D(double (&D)[3][3]) const {
@@ -660,18 +665,22 @@ __device__ __forceinline__ void phase_a_core(const View& v, const int tid, const
           lds2(stage_idx(CAP, 0, 0, tid), D[0][0], D[0][1]); lds2(stage_idx(CAP, 0, 1, tid), D[0][2], D[1][0]);
           lds2(stage_idx(CAP, 0, 2, tid), D[1][1], D[1][2]); lds2(stage_idx(CAP, 0, 3, tid), D[2][0], D[2][1]);
           lds2(stage_idx(CAP, 0, 4, tid), D[2][2], t);
+#ifndef NS_PARK_D_ONLY
           // the z components of the three parked gradients ride in block 0's pieces 4 and 5, which block 0 overwrites when it is
           // emitted: move them next to the x / y components (piece 6 of their own blocks)
           double g2, g3;
           lds2(stage_idx(CAP, 0, 5, tid), g2, g3);
           sts2(stage_idx(CAP, 1, 6, tid), t, 0.0); sts2(stage_idx(CAP, 2, 6, tid), g2, 0.0); sts2(stage_idx(CAP, 3, 6, tid), g3, 0.0);
 #endif
+#endif
         }
         __device__ void get_g(int n, double (&gn)[3]) const {
-#ifndef NS_NO_PARK
+#if !defined(NS_NO_PARK) && !defined(NS_PARK_D_ONLY)
           double pad;
           lds2(stage_idx(CAP, n, 5, tid), gn[0], gn[1]);
           lds2(stage_idx(CAP, n, 6, tid), gn[2], pad);
+#else
+          (void)n; (void)gn;
 #endif
         }
         // 128-bit shared accesses the compiler neither widens, splits nor forwards from registers
