@@ -174,7 +174,7 @@ const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx);
 const char* nsgpu_last_spmv_name(const nsgpu_ctx* ctx);
 
 /* Time on ctx's stream, CUDA events: ms of the last call of each phase.
- * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build. */
+ * 0 jacobian+residual kernel(s), 1 residual-only kernel(s), 2 spmv kernel, 3 halo, 4 h2d, 5 d2h, 6 pattern build, 7 streamline kernel. */
 int nsgpu_timers(nsgpu_ctx* ctx, double* ms, int n);
 /* Measured FP64 ceiling of ctx's GPU: DFMA TFLOP/s of a register-resident loop (8 chains/thread, 64 warps/SM), the
  * denominator of the benchmark's fp64 fraction (SURVEY 8d asks for a measured DFMA peak). Takes ~20 ms. */
@@ -215,6 +215,26 @@ int nsgpu_local_sizes(nsgpu_ctx* ctx, int64_t* n_owned, int64_t* n_ghost, int64_
  * idx_out; idx_out == NULL only fills start_out / ptr_out (size query). */
 int nsgpu_get_rows(nsgpu_ctx* ctx, int64_t n, const int32_t* rows, int64_t* start_out, int64_t* ptr_out, int32_t* idx_out,
                    int64_t idx_capacity);
+
+/* ---- streamline tracing (NavierStokes/streamtrace.py) -------------------------------------------------
+ * One GPU thread integrates one seed with scipy's RK45 algorithm (solve_ivp(..., method='RK45', events=..., max_step=...)),
+ * locating the point in the tetrahedral mesh of nsgpu_set_mesh and evaluating the P1 velocity there; zero outside the mesh.
+ *
+ * nsgpu_trace_setup  builds the point locator (first call / new tol) and loads the nodal velocity u_nodes (n_nodes x 3, the
+ *                    geometry-node order of nsgpu_set_mesh; NULL keeps the previous field).  Replaces geometry.bb_tree(mesh, 3)
+ *                    (streamtrace.py:397) and the Function uh filled by read_mesh_and_function (:57-129).  tol: a point is inside
+ *                    a cell when every barycentric coordinate is >= -tol.
+ * nsgpu_trace_velocity = velfunc (streamtrace.py:144-158) on n points: vel (n x 3), cell (n, -1 outside; may be NULL).
+ * nsgpu_trace_run    = streamtrace_pool (:198-218, reverse = 0: events |u| - speed_min falling, x - x_stop rising) or
+ *                    reverse_streamtrace_pool (:357-384, reverse = 1: velocity negated, x - x_stop falling) for n seeds at once.
+ *                    end_xyz (n x 3) = sol.y[:, -1]; status per seed: 0 reached t_end, 1 position event, 2 speed event,
+ *                    -1 step size underflow, -2 max_steps accepted steps; t_final / n_steps may be NULL.  The reference's values:
+ *                    x_stop 3.7 / 0.13, speed_min 1e-6, t_end 20, max_step 0.125, rtol 1e-3, atol 1e-6 (scipy defaults). */
+int nsgpu_trace_setup(nsgpu_ctx* ctx, const double* u_nodes, double tol);
+int nsgpu_trace_velocity(nsgpu_ctx* ctx, int64_t n, const double* points, double* vel, int32_t* cell);
+int nsgpu_trace_run(nsgpu_ctx* ctx, int64_t n, const double* seeds, int reverse, double x_stop, double speed_min, double t_end,
+                    double max_step, double rtol, double atol, int64_t max_steps, double* end_xyz, int32_t* status, double* t_final,
+                    int32_t* n_steps);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,9 @@ SIGNATURES = {
     "nsgpu_local_sizes": (ctypes.c_int, [c_ctx, c_i64p, c_i64p, c_i64p]),
     "nsgpu_get_rows": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "nsgpu_add_pattern_entries": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "nsgpu_trace_setup": (ctypes.c_int, [c_ctx, ctypes.c_void_p, ctypes.c_double]),
+    "nsgpu_trace_velocity": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nsgpu_trace_run": (ctypes.c_int, [c_ctx, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int64] + [ctypes.c_void_p] * 4),
 }
 
 

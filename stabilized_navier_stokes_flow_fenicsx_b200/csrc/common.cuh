@@ -81,6 +81,7 @@ struct nsgpu_ctx {
   bool rows_presorted = false;      // column blocks of each row are contiguous per neighbour entity, in pair order
   struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
   void* krylov = nullptr;                      // work vectors of the device-resident TFQMR (krylov.cu)
+  void* trace = nullptr;                       // locator + velocity tables of the streamline tracer (streamtrace.cu)
 
   // internal numbering (renumber.cu): caller local dof d <-> internal dof d_perm[d]; d_perm == nullptr means identity
   int renumber = 1;         // option: 0 never, 1 when the caller's numbering is not vertex-blocked, 2 always
@@ -198,6 +199,8 @@ int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
 int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
 int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out);
 void krylov_free(nsgpu_ctx* ctx);
+// streamtrace.cu
+void trace_free(nsgpu_ctx* ctx);
 // renumber.cu
 int renumber_build(nsgpu_ctx* ctx);
 int renumber_extend_cols(nsgpu_ctx* ctx, int64_t n_extra, const int32_t* leader_local, const int32_t* slot, const int32_t* size,

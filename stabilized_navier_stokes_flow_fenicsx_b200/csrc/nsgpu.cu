@@ -150,6 +150,7 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
   krylov_free(ctx);
+  trace_free(ctx);
   renumber_free(ctx);
   cudaFree(ctx->d_nonfinite);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -178,6 +179,7 @@ int nsgpu_set_mesh(nsgpu_ctx* ctx, int gdim, int64_t n_nodes, const double* x, i
   NS_REQUIRE(ctx, x && x_dofmap && n_nodes > 0 && n_cells_owned >= 0 && n_cells_total >= n_cells_owned, "set_mesh: bad sizes or NULL arrays");
   ctx->gdim = gdim; ctx->n_nodes = n_nodes; ctx->n_cells_owned = n_cells_owned; ctx->n_cells_total = n_cells_total;
   ctx->pattern_built = false;
+  trace_free(ctx);
   for (int k = 0; k < 3; ++k) { ctx->bbox_lo[k] = x[k]; ctx->bbox_hi[k] = x[k]; }
   for (int64_t i = 1; i < n_nodes; ++i)
     for (int k = 0; k < 3; ++k) {
