@@ -160,14 +160,16 @@ int nsgpu_host_free_pinned(void* p);
 
 /* Options: "kernel" (NSGPU_KERNEL_*); for the factorised P1-P1 kernels "ws" (1, default: warp-specialised kernel -- two
  * compute warpgroups and a gather warpgroup per SM, tables by cp.async.bulk) and "pipe" (1: software-pipelined 2-CTA kernel
- * when "ws" is off or does not apply; both 0: plain tile kernel); "fuse_fj", "stream_host", "stream_chunks", "spmv_blocks";
+ * when "ws" is off or does not apply; both 0: plain tile kernel); "rowown" (atomics-free row-owner kernel for the spaces /
+ * forms without a factorised kernel: 0 never, 1 default: P2-P1 spaces, 2 every such space); "fuse_fj", "stream_host", "stream_chunks", "spmv_blocks";
  * "check_finite" (1, default: NaN / Inf scan of every assembled residual, status NSGPU_ENONFINITE);
  * "renumber" (0 never, 1 default: internal vertex-blocked numbering when the caller's W.dofmap.list is not vertex-blocked,
  * 2 always) and "renumber_order" (1 leader-dof order, 2 default: Morton order of the vertices) -- both before nsgpu_set_space. */
 int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value);
 
 /* Which assembly kernel variant the last residual / Jacobian call ran: "p1tet_ws", "p1tet_ws (streamed host vectors)",
- * "p1tet_pipe", "p1tet_pipe (streamed host vectors)", "p1tet_tiles", "generic_coop", "generic_row" (static string, never NULL). */
+ * "p1tet_pipe", "p1tet_pipe (streamed host vectors)", "p1tet_tiles", "rowown", "generic_coop", "generic_row", "trace_rk45"
+ * (static string, never NULL). */
 const char* nsgpu_last_kernel_name(const nsgpu_ctx* ctx);
 /* Which MatMult kernel the last nsgpu_spmv* / Krylov product ran: "spmv_block4" (vertex-blocked 4x4 blocks, one column index
  * per block) or "spmv_csr". */

@@ -264,7 +264,10 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   // With several ranks the entries that receive contributions of other ranks' ghost rows (the J.assemble() exchange adds
   // into them, and some of them are entries no local cell touches) are the only ones that have to start from zero: they are
   // exactly the receive positions of the ghost-row plan, a few 10 MB instead of the whole value array.
-  const bool zero_vals = want_J && !(fast && ctx->extra_rows.empty());
+  // The row-owner kernel of the other element pairs / forms (rowown.cu) writes whole rows, including the entries only other
+  // ranks contribute to, so it never needs the zero-fill.
+  const bool rowown = !fast && ctx->kernel_sel == NSGPU_KERNEL_AUTO && rowown_available(ctx);
+  const bool zero_vals = want_J && !rowown && !(fast && ctx->extra_rows.empty());
   const bool zero_recv_only = zero_vals && fast && ctx->rows.n_neigh > 0 && !ctx->rows.recv_ptr.empty() && ctx->rows.recv_ptr.back() > 0;
   if (zero_recv_only) {
     const int64_t nr = ctx->rows.recv_ptr.back();
@@ -317,6 +320,10 @@ int assemble_impl(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F,
   }
   if (fast) {
     int rc = p1tet_assemble(ctx, d_xin, want_J, want_F, d_Fout);
+    if (rc != NSGPU_OK) return rc;
+  } else if (rowown) {
+    ctx->last_kernel = "rowown";
+    const int rc = rowown_assemble(ctx, d_xin, want_J, want_F, d_Fout);
     if (rc != NSGPU_OK) return rc;
   } else {
     const int key = ctx->gdim * 10 + ctx->vdeg;

@@ -81,6 +81,7 @@ struct nsgpu_ctx {
   bool rows_presorted = false;      // column blocks of each row are contiguous per neighbour entity, in pair order
   struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
   void* krylov = nullptr;                      // work vectors of the device-resident TFQMR (krylov.cu)
+  void* rowown_plan = nullptr;                 // entity incidence lists + point records of the row-owner kernel (rowown.cu)
   void* trace = nullptr;                       // locator + velocity tables of the streamline tracer (streamtrace.cu)
 
   // internal numbering (renumber.cu): caller local dof d <-> internal dof d_perm[d]; d_perm == nullptr means identity
@@ -107,6 +108,7 @@ struct nsgpu_ctx {
   int kernel_sel = NSGPU_KERNEL_AUTO;
   int n_sms = 148;     // SM count of the device (nsgpu_create)
   int ws = 1;          // row-owner kernel: warp-specialised variant (two compute warpgroups + one gather warpgroup per SM) when it applies
+  int rowown = 1;      // atomics-free row-owner kernel (rowown.cu): 0 never (cooperative kernel with atomics), 1 for P2-P1 spaces, 2 for every space without a factorised kernel
   int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
   int fuse_fj = 0;     // nsgpu_residual also assembles J (one pass) and nsgpu_jacobian reuses it when called with the same state
   bool jac_valid = false;      // d_vals holds the Jacobian of the state saved in d_x_last
@@ -199,6 +201,10 @@ int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
 int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
 int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out);
 void krylov_free(nsgpu_ctx* ctx);
+// rowown.cu
+bool rowown_available(nsgpu_ctx* ctx);
+int rowown_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);
+void rowown_free(nsgpu_ctx* ctx);
 // streamtrace.cu
 void trace_free(nsgpu_ctx* ctx);
 // renumber.cu

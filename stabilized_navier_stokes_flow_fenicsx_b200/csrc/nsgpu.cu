@@ -150,6 +150,7 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
   krylov_free(ctx);
+  rowown_free(ctx);
   trace_free(ctx);
   renumber_free(ctx);
   cudaFree(ctx->d_nonfinite);
@@ -695,6 +696,9 @@ int nsgpu_set_option(nsgpu_ctx* ctx, const char* name, int64_t value) {
     ctx->stream_host = value != 0;
   } else if (!strcmp(name, "pipe")) {
     ctx->pipe = value != 0;
+  } else if (!strcmp(name, "rowown")) {
+    NS_REQUIRE(ctx, value >= 0 && value <= 2, "set_option: rowown must be 0 (never), 1 (P2-P1 spaces) or 2 (every space without a factorised kernel)");
+    ctx->rowown = (int)value;
   } else if (!strcmp(name, "overlap")) {
     ctx->overlap = value != 0;
   } else if (!strcmp(name, "sm_reserve")) {

@@ -75,6 +75,8 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     gF = asm.residual(w)
     assert np.abs(gv - vals).max() <= RTOL * np.abs(vals).max()
     assert np.abs(gF - F).max() <= RTOL * np.abs(F).max()
+    # which kernel ran: the factorised P1-P1 tet kernel for the flagship form, the atomics-free row-owner kernel for every other pair / form
+    assert asm.last_kernel_name() == ("p1tet_ws" if kind.startswith("duct_p1") else ("rowown" if sp.vdeg == 2 else "generic_coop"))
     gv2, gF2 = asm.jacobian_residual(w)              # fused pass gives the same numbers
     assert np.abs(gv2 - vals).max() <= RTOL * np.abs(vals).max()
     assert np.abs(gF2 - F).max() <= RTOL * np.abs(F).max()
@@ -83,6 +85,33 @@ def test_pattern_bit_exact_and_entries_match(oracle, kind):
     y = asm.mult(xv)
     yo = oracle.spmv(indptr, indices, vals, xv)
     assert np.abs(y - yo).max() <= RTOL * np.abs(yo).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("kind", ["duct_p2", "cavity_ugn", "cavity_ugn_p2", "stokes_duct_p2", "stokes_channel"])
+def test_rowowner_kernel_writes_every_entry_once_and_is_reproducible(oracle, kind):
+    """The row-owner kernel (rowown.cu) needs no zero-fill: poisoned values are all overwritten; two runs agree bitwise; the
+    cooperative kernel with atomics (option rowown = 0) gives the same numbers to rounding."""
+    m, sp, w, bcs, fk = _case(kind)
+    asm = _gpu(m, sp, bcs, fk)
+    asm.set_option("rowown", 2)                            # also for the P1-P1 spaces (default: P2-P1 only)
+    gp, gi = asm.create_matrix()
+    asm.set_values(np.full(asm.nnz, np.nan))
+    v1, F1 = asm.jacobian_residual(w)
+    assert asm.last_kernel_name() == "rowown"
+    assert np.isfinite(v1).all() and np.isfinite(F1).all()
+    asm.set_values(np.full(asm.nnz, 7.0))
+    v2, F2 = asm.jacobian_residual(w)
+    assert np.array_equal(v1, v2) and np.array_equal(F1, F2)
+    Fo = asm.residual(w)                                   # residual-only pass: same entries
+    assert np.abs(Fo - F1).max() <= 1e-14 * np.abs(F1).max()
+    asm.set_option("rowown", 0)
+    v3, F3 = asm.jacobian_residual(w)
+    assert asm.last_kernel_name() == "generic_coop"
+    assert np.abs(v3 - v1).max() <= RTOL * np.abs(v1).max() and np.abs(F3 - F1).max() <= RTOL * np.abs(F1).max()
+    if oracle is not None:                                 # and the oracle, entry by entry
+        indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+        assert np.abs(v1 - vals).max() <= RTOL * np.abs(vals).max() and np.abs(F1 - F).max() <= RTOL * np.abs(F).max()
     asm.close()
 
 

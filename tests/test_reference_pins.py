@@ -46,7 +46,9 @@ def test_duct_stokes_outlet_is_the_fully_developed_square_duct_profile():
     influx, area = P.plane_flux(m, sp, w, 0.0)
     outflux, area_o = P.plane_flux(m, sp, w, 4.0)
     assert abs(area - 1.0) < 1e-12 and abs(area_o - 1.0) < 1e-12
-    assert abs(outflux - influx) < 1e-9 * abs(influx)                 # Taylor-Hood: q = 1 is a test function, the net flux is zero
+    # Taylor-Hood conserves mass against every pressure test function; the outlet pressure dofs are Dirichlet rows (p = 0), so
+    # q = 1 is not one of them and the net flux vanishes only up to the divergence in the last cell layer (oracle: -2.0e-4)
+    assert abs(outflux - influx) < 5e-4 * abs(influx)
     X, c = sp.dof_x, sp.dof_comp
     ctr = np.flatnonzero((c == 0) & (np.abs(X[:, 0] - 4.0) < 1e-12) & (np.abs(X[:, 1]) < 1e-12) & (np.abs(X[:, 2]) < 1e-12))
     ratio = w[ctr[0]] / (outflux / area_o)
