@@ -287,12 +287,16 @@ def run_ours(args):
     snes_ms = comm.max(1e3 * (time.perf_counter() - t0) / e2e_steps)
     asm.set_option("fuse_fj", 0)
     asm.jacobian_residual_dev(x_dev, True, F_dev)
-    k_its = 5
     asm.tfqmr_dev(F_dev, y_dev, rtol=0.0, max_it=1, pc=4)          # allocate work vectors
-    asm.sync(); comm.barrier()
-    t0 = time.perf_counter()
-    kinfo = asm.tfqmr_dev(F_dev, y_dev, rtol=0.0, max_it=k_its, pc=4)
-    tfqmr_ms = comm.max(1e3 * (time.perf_counter() - t0) / max(kinfo["its"], 1))
+    tk = []
+    for k_its in (2, 17):                                          # marginal cost of an iteration: (t(17) - t(2)) / 15
+        asm.sync(); comm.barrier()
+        t0 = time.perf_counter()
+        kinfo = asm.tfqmr_dev(F_dev, y_dev, rtol=0.0, max_it=k_its, pc=4)
+        tk.append((kinfo["its"], comm.max(1e3 * (time.perf_counter() - t0))))
+    tfqmr_ms = (tk[1][1] - tk[0][1]) / max(tk[1][0] - tk[0][0], 1)
+    tfqmr_solve_overhead_ms = tk[0][1] - tk[0][0] * tfqmr_ms       # set-up product, preconditioner extraction, true-residual check
+    other = other_paths() if (world == 1 and not args.no_extras) else None
 
     nc_total = 6 * n_cross * n_cross * n_long
     nv_total = (n_cross + 1) ** 2 * (n_long + 1)
@@ -344,9 +348,12 @@ def run_ours(args):
             "snes_iterate": {"ms": snes_ms, "what": "NonlinearPDE_SNESProblem-style callback pair per Newton iterate: nsgpu_residual(x_host) -> F_host "
                                                       "then nsgpu_jacobian(x_host) (J stays resident), option fuse_fj: the residual pass assembles J, the Jacobian "
                                                       "call recognises the state on the device and reuses it"},
-            "tfqmr": {"ms_per_iteration": tfqmr_ms, "iterations_timed": kinfo["its"], "pc": "4x4 vertex-block Jacobi",
-                      "what": "device-resident KSPTFQMR iteration on the resident Jacobian: 2 MatMult + fused vector updates / reductions; "
-                              "includes the set-up product and the true-residual check amortised over the timed iterations"},
+            "tfqmr": {"ms_per_iteration": tfqmr_ms, "iterations_timed": tk[1][0] - tk[0][0], "pc": "4x4 vertex-block Jacobi",
+                      "per_solve_overhead_ms": tfqmr_solve_overhead_ms,
+                      "what": "device-resident KSPTFQMR iteration on the resident Jacobian: 2 MatMult + fused vector updates / reductions "
+                              "(marginal cost: the difference of a 17- and a 2-iteration solve); per_solve_overhead_ms = preconditioner extraction, "
+                              "the set-up product and the true-residual check of one solve"},
+            "other_paths": other,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -358,6 +365,45 @@ def run_ours(args):
         asm.dev_free(p)
     asm.close()
     comm.close()
+
+
+def other_paths():
+    """The other hot-path rows of SURVEY section 8 on small fixed inputs (1 GPU): the second element pair and the streamline tracer."""
+    from stabilized_navier_stokes_flow_fenicsx_b200 import mesh as M
+    from stabilized_navier_stokes_flow_fenicsx_b200 import streamtrace as ST
+    from stabilized_navier_stokes_flow_fenicsx_b200.assembler import NSAssembler
+    out = {}
+    m = M.duct_mesh(24, 48); sp = M.mixed_space(m, 2)
+    a2 = NSAssembler(m.x, m.cells, sp.dofmap, vdeg=2)
+    a2.set_form(flavour=0, nu=1.0 / 50); a2.set_bcs(M.duct_bcs(sp))
+    a2.create_matrix(fetch=False)
+    xd, Fd = a2.dev_alloc(8 * a2.n_cols), a2.dev_alloc(8 * a2.n_cols)
+    a2.h2d(xd, M.duct_state(sp))
+    ts = []
+    for it in range(8):
+        a2.jacobian_residual_dev(xd, True, Fd)
+        if it >= 3:
+            ts.append(a2.last_kernel_ms())
+    ms = float(np.median(ts))
+    out["p2p1_gmetric"] = {"cells": m.n_cells, "nnz": int(a2.nnz), "kernel": a2.last_kernel_name(), "jf_ms": ms, "Mcells/s": m.n_cells / ms / 1e3,
+                           "what": "fused J+F on P2-P1 Taylor-Hood tets (BASELINE config 4 pair), atomics-free row-owner kernel"}
+    a2.close()
+    m = M.duct_mesh(10, 40)
+    y, z = m.x[:, 1], m.x[:, 2]
+    prof = (1 - 4 * y * y) * (1 - 4 * z * z)
+    u = np.column_stack((1.5 * prof + 0.02, -0.6 * z * prof, 0.6 * y * prof))
+    tr = ST.StreamTracer(m.x, m.cells, u)
+    rng = np.random.default_rng(5)
+    seeds = np.hstack((np.full((40000, 1), 0.3), rng.uniform(-0.3, 0.3, size=(40000, 2))))
+    tr.trace(seeds[:256])
+    t0 = time.perf_counter()
+    end, status, tf, ns = tr.trace(seeds)
+    dt = time.perf_counter() - t0
+    out["streamtrace"] = {"seeds": 40000, "cells": m.n_cells, "ms_host_to_host": 1e3 * dt, "kernel_ms": tr.last_kernel_ms(), "seeds_per_s": 40000 / dt,
+                          "accepted_steps": int(ns.sum()), "reached_x_3.7": int((status == 1).sum()),
+                          "what": "streamtrace.py's 40 000 seeds (RK45, rtol 1e-3, max_step 0.125, events) in one nsgpu_trace_run call"}
+    tr.close()
+    return out
 
 
 def asm_kernel_name(asm):
@@ -376,6 +422,7 @@ def main():
     ap.add_argument("--pipe", type=int, default=None, help="0: do not use the software-pipelined variant either (plain tile kernel)")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the small P2-P1 / streamline-tracer measurements (other_paths)")
     ap.add_argument("--no-aij", action="store_true", help="skip the AIJ-mode end-to-end step (values to pinned host memory)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
