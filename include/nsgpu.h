@@ -118,7 +118,8 @@ int nsgpu_spmv(nsgpu_ctx* ctx, const double* x_local, double* y_owned);
 /* KSPSolve with KSPTFQMR (snes_ksp_type 'tfqmr', NavierStokesChannelFlow.py:77, :282-283; KSP rtol :285) on the
  * Jacobian of the last nsgpu_jacobian*: transpose-free QMR, right-preconditioned, every vector and scalar
  * device-resident; two MatMults per iteration, dot products reduced over all ranks (ncclAllReduce).
- *   pc: 0 none, 1 Jacobi, 4 = 4x4 block Jacobi over the dofs of one P1-P1 vertex (falls back to 1 elsewhere).
+ *   pc: 0 none, 1 Jacobi, 4 = 4x4 block Jacobi over the dofs of one P1-P1 vertex (falls back to 1 elsewhere),
+ *       5 = multicolour 4x4-block ILU(0), block Jacobi over the ranks (P1-P1 tets; NSGPU_EUNSUPPORTED elsewhere).
  *   zero_guess != 0 ignores the incoming x (PETSc's default initial guess).
  * Stops when the quasi-residual bound tau*sqrt(m+1) <= max(rtol * ||b||, atol) (PETSc's default test) or after max_it iterations;
  * *its_out = iterations done, *rnorm_out = TRUE residual norm ||b - A x|| at exit, *r0norm_out = ||b - A x0||.
@@ -129,6 +130,13 @@ int nsgpu_tfqmr_dev(nsgpu_ctx* ctx, const double* b_owned_dev, double* x_local_d
                     int zero_guess, int* its_out, double* rnorm_out, double* r0norm_out);
 /* The two vector operations a device-resident Newton loop needs besides F, J and the solve (VecAXPY / VecNorm on
  * the owned entries; the norm is reduced over all ranks): y += a x, *out = ||x||_2. */
+/* Multicolour 4x4-block ILU(0) of the resident Jacobian (pc = 5 of nsgpu_tfqmr*; the class of PETSc's default PC for
+ * snes_ksp_type = 'tfqmr', NavierStokesChannelFlow.py:282-291: ILU(0), block Jacobi over the ranks).  nsgpu_ilu_apply = PCApply on
+ * host vectors (owned entries): z = U^-1 L^-1 r; refactor != 0 factorises the current values first (always done when there is no
+ * factorisation yet).  nsgpu_ilu_colours: the elimination colour of every owned vertex in the library's internal vertex order
+ * (= the caller's order when its numbering is vertex-blocked, dof = 4 vertex + component) and the number of colours; for tests. */
+int nsgpu_ilu_apply(nsgpu_ctx* ctx, int refactor, const double* r_owned, double* z_owned);
+int nsgpu_ilu_colours(nsgpu_ctx* ctx, int32_t* colour /* n_owned / 4, may be NULL */, int32_t* n_colours);
 int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev);
 int nsgpu_norm_dev(nsgpu_ctx* ctx, const double* x_dev, double* out);
 /* VecDot over the owned entries, reduced over all ranks (the initial slope F . J dx of SNES' backtracking line search). */

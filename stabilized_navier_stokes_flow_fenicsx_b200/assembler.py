@@ -217,6 +217,22 @@ class NSAssembler:
                                              ctypes.byref(its), ctypes.byref(rn), ctypes.byref(r0)), "tfqmr_dev")
         return {"its": its.value, "rnorm": rn.value, "r0norm": r0.value}
 
+    def ilu_apply(self, r, refactor=True):
+        """PCApply of the multicolour block ILU(0) (pc = 5) on a host vector: z = U^-1 L^-1 r (owned entries)."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        if r.size < self.n_owned:
+            raise ValueError(f"ilu_apply needs the {self.n_owned} owned entries")
+        z = np.empty(self.n_owned)
+        self._check(self.lib.nsgpu_ilu_apply(self.ctx, 1 if refactor else 0, _ptr(r), _ptr(z)), "ilu_apply")
+        return z
+
+    def ilu_colours(self):
+        """(elimination colour per owned vertex in the internal vertex order, number of colours)"""
+        n = ctypes.c_int32()
+        col = np.empty(self.n_owned // 4, dtype=np.int32)
+        self._check(self.lib.nsgpu_ilu_colours(self.ctx, _ptr(col), ctypes.byref(n)), "ilu_colours")
+        return col, n.value
+
     def axpy_dev(self, a, x_dev, y_dev):
         self._check(self.lib.nsgpu_axpy_dev(self.ctx, float(a), x_dev, y_dev), "axpy_dev")
 

@@ -81,6 +81,7 @@ struct nsgpu_ctx {
   bool rows_presorted = false;      // column blocks of each row are contiguous per neighbour entity, in pair order
   struct nsgpu_p1tet_plan* p1plan = nullptr;   // factorised P1-P1 tet kernels (p1tet.cu)
   void* krylov = nullptr;                      // work vectors of the device-resident TFQMR (krylov.cu)
+  void* ilu = nullptr;                         // colouring + factors of the multicolour block ILU(0) preconditioner (ilu.cu)
   void* rowown_plan = nullptr;                 // entity incidence lists + point records of the row-owner kernel (rowown.cu)
   void* trace = nullptr;                       // locator + velocity tables of the streamline tracer (streamtrace.cu)
 
@@ -201,6 +202,11 @@ int norm_impl(nsgpu_ctx* ctx, const double* d_x, double* out);
 int norm_n_impl(nsgpu_ctx* ctx, const double* d_x, int64_t n, double* out);
 int dot_impl(nsgpu_ctx* ctx, const double* d_x, const double* d_y, double* out);
 void krylov_free(nsgpu_ctx* ctx);
+// ilu.cu
+int ilu_factor(nsgpu_ctx* ctx);
+int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z);
+int ilu_colours(nsgpu_ctx* ctx, int32_t* h_colour, int32_t* n_colours);
+void ilu_free(nsgpu_ctx* ctx);
 // rowown.cu
 bool rowown_available(nsgpu_ctx* ctx);
 int rowown_assemble(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool want_F, double* d_Fout);

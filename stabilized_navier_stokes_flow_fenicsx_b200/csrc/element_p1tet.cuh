@@ -397,5 +397,9 @@ int p1tet_build_plan(nsgpu_ctx* ctx);
 void p1tet_free(nsgpu_ctx* ctx);
 void p1tet_mark_bc_dirty(nsgpu_ctx* ctx);
 int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y);
+// the vertex-blocked view of the CSR matrix the block SpMV walks (also used by the block ILU, ilu.cu): per vertex the start of its
+// neighbour list in ctx->d_pairs, the number of neighbours, the CSR starts of its four rows and its four dofs
+struct P1BlockView { int64_t n_ent; const int64_t* pair0; const int32_t* ns; const int64_t* rowpos; const int32_t* rowdof; };
+bool p1tet_block_view(nsgpu_ctx* ctx, P1BlockView* out);
 int p1tet_assemble_streamed(nsgpu_ctx* ctx, const double* x_host, double* F_host);
 }  // namespace nsgpu

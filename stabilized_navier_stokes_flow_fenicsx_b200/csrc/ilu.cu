@@ -1,0 +1,435 @@
+// ilu.cu -- multicolour block ILU(0) preconditioner for the device-resident KSPTFQMR.
+//
+// The reference leaves the preconditioner of snes_ksp_type = 'tfqmr' at PETSc's default (NavierStokes/NavierStokesChannelFlow.py:
+// 282-291): ILU(0) on one rank, block Jacobi with ILU(0) on each rank's diagonal block under mpirun.  This is that class of
+// preconditioner in a form a GPU can run: the incomplete factorisation works on the 4x4 vertex blocks of the P1-P1 matrix (the
+// velocity components and the pressure of a vertex are eliminated together) in a multicolour elimination order -- vertices of one
+// colour share no matrix entry, so a colour is factorised, and later substituted, by one kernel launch with one thread group
+// per vertex.  Couplings to other ranks' vertices are dropped (block Jacobi over the ranks, as PETSc does).
+//
+//   colouring   Jones-Plassmann with hashed priorities on the vertex graph of the owned rows (deterministic), <= 64 colours
+//   order       elimination order = (colour, vertex)
+//   factorise   for colour c, vertex i:  for every neighbour k with colour < c, in elimination order:
+//                   L_ik = A_ik U_kk^-1 ;  A_ij -= L_ik U_kj  for the blocks (i, j) of the pattern with j after k    [ILU(0)]
+//               then U_ii^-1 by Gauss-Jordan with partial pivoting
+//   apply       z = U^-1 L^-1 r: one launch per colour forwards (unit lower factor), one per colour backwards
+//
+// Block access is the vertex-blocked view the block SpMV uses (p1tet.cu): per vertex the list of neighbour vertices
+// (ctx->d_pairs) and the CSR starts of its four rows, blocks of four contiguous values per row.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "element_p1tet.cuh"
+
+namespace nsgpu {
+
+struct IluPlan {
+  int64_t nv = 0;                  // owned vertices
+  int n_colours = 0;
+  int32_t* d_colour = nullptr;     // per owned vertex
+  int32_t* d_order = nullptr;      // vertices sorted by (colour, vertex)
+  std::vector<int64_t> cstart;     // n_colours + 1 offsets into d_order
+  double* d_lu = nullptr;          // 16 doubles per (vertex, neighbour) pair, row-major 4x4, indexed like ctx->d_pairs
+  double* d_dinv = nullptr;        // 16 doubles per vertex: U_ii^-1
+  bool unsupported = false;
+};
+
+__device__ __forceinline__ uint32_t ilu_hash(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void k_ilu_check(int64_t nv, const int32_t* __restrict__ rowdof, int* bad) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < nv && rowdof[4 * e] != (int32_t)(4 * e)) *bad = 1;
+}
+
+// one Jones-Plassmann round: an uncoloured vertex whose priority beats every uncoloured neighbour takes the lowest free colour
+__global__ void k_ilu_colour(int64_t nv, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
+                             const uint64_t* __restrict__ pairs, const int32_t* __restrict__ colour, int32_t* colour_out, unsigned long long* left,
+                             int* too_many) {
+  // decisions are taken on the colours at the start of the round (colour), results go to colour_out: the colouring does not
+  // depend on the order in which the threads run
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nv || colour[e] >= 0) return;
+  const uint32_t pe = ilu_hash((uint32_t)e);
+  unsigned long long used = 0;
+  const int64_t p0 = pair0[e];
+  const int n = ns[e];
+  for (int s = 0; s < n; ++s) {
+    const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
+    if (B >= n_owned) continue;
+    const int64_t k = B >> 2;
+    if (k == e) continue;
+    const int ck = colour[k];
+    if (ck >= 0) { used |= 1ull << ck; continue; }
+    const uint32_t pk = ilu_hash((uint32_t)k);
+    if (pk > pe || (pk == pe && k > e)) { atomicAdd(left, 1ull); return; }   // a neighbour goes first
+  }
+  int c = 0;
+  while (c < 64 && ((used >> c) & 1ull)) ++c;
+  if (c >= 64) { *too_many = 1; c = 63; }
+  colour_out[e] = c;
+}
+
+__global__ void k_ilu_keys(int64_t nv, const int32_t* __restrict__ colour, uint64_t* keys) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < nv) keys[e] = ((uint64_t)(uint32_t)colour[e] << 32) | (uint64_t)e;
+}
+
+__global__ void k_ilu_order(int64_t nv, const uint64_t* __restrict__ keys, int32_t* order, unsigned long long* count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  order[i] = (int32_t)(keys[i] & 0xffffffffu);
+  atomicAdd(count + (keys[i] >> 32), 1ull);
+}
+
+// LU blocks <- the owned x owned blocks of the assembled Jacobian
+__global__ void k_ilu_load(int64_t nv, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
+                           const uint64_t* __restrict__ pairs, const int64_t* __restrict__ rowpos, const double* __restrict__ vals, double* __restrict__ lu) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t >> 4;
+  const int lane = (int)(t & 15);
+  if (e >= nv) return;
+  const int64_t p0 = pair0[e];
+  const int n = ns[e];
+  for (int s = lane; s < n; s += 16) {
+    const bool own = (int64_t)(pairs[p0 + s] & 0xffffffffu) < n_owned;
+    double* o = lu + 16 * (p0 + s);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double* v = vals + rowpos[4 * e + c] + 4 * s;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) o[4 * c + d] = own ? v[d] : 0.0;
+    }
+  }
+}
+
+__device__ __forceinline__ void blk_load(const double* p, double (&A)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) A[r][c] = p[4 * r + c];
+}
+__device__ __forceinline__ void blk_store(double* p, const double (&A)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[4 * r + c] = A[r][c];
+}
+
+__device__ bool blk_inverse(double (&A)[4][4], double (&B)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) B[r][c] = (r == c) ? 1.0 : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int piv = k;
+    double best = fabs(A[k][k]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r > k && fabs(A[r][k]) > best) { best = fabs(A[r][k]); piv = r; }
+    if (best == 0.0 || !isfinite(best)) { ok = false; break; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r == piv && piv != k) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { double t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; t = B[k][c]; B[k][c] = B[r][c]; B[r][c] = t; }
+      }
+    const double ip = 1.0 / A[k][k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { A[k][c] *= ip; B[k][c] *= ip; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r != k) {
+        const double f = A[r][k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { A[r][c] -= f * A[k][c]; B[r][c] -= f * B[k][c]; }
+      }
+  }
+  if (!ok) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) B[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  return ok;
+}
+
+// factorise the vertices order[i0 .. i1) (one colour).  One thread per vertex.
+__global__ void __launch_bounds__(64)
+k_ilu_factor(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __restrict__ order, const int32_t* __restrict__ colour,
+             const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, double* lu, double* dinv,
+             int* singular) {
+  const int64_t idx = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= i1) return;
+  const int64_t i = order[idx];
+  const int64_t p0 = pair0[i];
+  const int n = ns[i];
+  int sdiag = -1;
+  // eliminate the earlier neighbours in elimination order (colour, vertex): repeated selection of the smallest unprocessed one
+  long long last = -1;    // key of the neighbour processed last
+  for (;;) {
+    long long best = -1;
+    int sb = -1;
+    for (int s = 0; s < n; ++s) {
+      const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
+      if (B >= n_owned) continue;
+      const int64_t k = B >> 2;
+      if (k == i) { sdiag = s; continue; }
+      const int ck = colour[k];
+      if (ck >= cc) continue;
+      const long long key = ((long long)ck << 32) | k;
+      if (key > last && (best < 0 || key < best)) { best = key; sb = s; }
+    }
+    if (sb < 0) break;
+    last = best;
+    const int64_t k = best & 0xffffffffLL;
+    const int ck = (int)(best >> 32);
+    // L_ik = A_ik U_kk^-1
+    double Aik[4][4], Dk[4][4], L[4][4];
+    blk_load(lu + 16 * (p0 + sb), Aik);
+    blk_load(dinv + 16 * k, Dk);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) L[r][c] = Aik[r][0] * Dk[0][c] + Aik[r][1] * Dk[1][c] + Aik[r][2] * Dk[2][c] + Aik[r][3] * Dk[3][c];
+    blk_store(lu + 16 * (p0 + sb), L);
+    // A_ij -= L_ik U_kj for the pattern blocks (i, j) with j after k
+    const int64_t q0 = pair0[k];
+    const int nk = ns[k];
+    for (int t = 0; t < n; ++t) {
+      const int64_t Bj = (int64_t)(pairs[p0 + t] & 0xffffffffu);
+      if (Bj >= n_owned) continue;
+      const int64_t j = Bj >> 2;
+      if (j == k) continue;
+      const int cj = j == i ? cc : colour[j];
+      if (cj < ck || (cj == ck && j < k)) continue;        // j before k: that block is an L block already final
+      // (k, j) in row k?  neighbour lists are sorted by first dof
+      int lo = 0, hi = nk - 1, u = -1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int64_t Bm = (int64_t)(pairs[q0 + mid] & 0xffffffffu);
+        if (Bm == Bj) { u = mid; break; }
+        if (Bm < Bj) lo = mid + 1; else hi = mid - 1;
+      }
+      if (u < 0) continue;
+      double U[4][4], A[4][4];
+      blk_load(lu + 16 * (q0 + u), U);
+      blk_load(lu + 16 * (p0 + t), A);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) A[r][c] -= L[r][0] * U[0][c] + L[r][1] * U[1][c] + L[r][2] * U[2][c] + L[r][3] * U[3][c];
+      blk_store(lu + 16 * (p0 + t), A);
+    }
+  }
+  double D[4][4], Di[4][4];
+  if (sdiag >= 0) blk_load(lu + 16 * (p0 + sdiag), D);
+  else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) D[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  if (!blk_inverse(D, Di)) *singular = 1;
+  blk_store(dinv + 16 * i, Di);
+}
+
+// one colour of the forward (LOWER: z_i -= sum over earlier neighbours L_ik z_k) or backward (z_i = U_ii^-1 (z_i - sum over later
+// neighbours U_ij z_j)) substitution, in place.  Sixteen lanes per vertex, lane s takes neighbour s.
+template <bool LOWER>
+__global__ void __launch_bounds__(256)
+k_ilu_sweep(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __restrict__ order, const int32_t* __restrict__ colour,
+            const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, const double* __restrict__ lu,
+            const double* __restrict__ dinv, double* z) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t idx = i0 + (t >> 4);
+  const int lane = (int)(t & 15);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int64_t i = 0;
+  if (idx < i1) {
+    i = order[idx];
+    const int64_t p0 = pair0[i];
+    const int n = ns[i];
+    for (int s = lane; s < n; s += 16) {
+      const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
+      if (B >= n_owned) continue;
+      const int64_t k = B >> 2;
+      if (k == i) continue;
+      const int ck = colour[k];
+      if (LOWER ? ck >= cc : ck <= cc) continue;
+      const double* M = lu + 16 * (p0 + s);
+      const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += M[4 * r] * z0 + M[4 * r + 1] * z1 + M[4 * r + 2] * z2 + M[4 * r + 3] * z3;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc[r] += __shfl_down_sync(0xffffffffu, acc[r], o, 16);
+  }
+  if (idx < i1 && lane == 0) {
+    double y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[r] = z[4 * i + r] - acc[r];
+    if (LOWER) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) z[4 * i + r] = y[r];
+    } else {
+      const double* D = dinv + 16 * i;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) z[4 * i + r] = D[4 * r] * y[0] + D[4 * r + 1] * y[1] + D[4 * r + 2] * y[2] + D[4 * r + 3] * y[3];
+    }
+  }
+}
+
+void ilu_free(nsgpu_ctx* ctx) {
+  IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
+  if (!P) return;
+  cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv);
+  delete P;
+  ctx->ilu = nullptr;
+}
+
+static inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n > 0 ? n : 1, 256); }
+
+// colouring and elimination order (once per pattern)
+static int ilu_plan(nsgpu_ctx* ctx, const P1BlockView& V) {
+  ilu_free(ctx);
+  IluPlan* P = new IluPlan();
+  ctx->ilu = P;
+  cudaStream_t s = ctx->stream;
+  const int64_t nv = ctx->n_owned / 4;
+  P->nv = nv;
+  int* d_flag = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+  void* d_tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(d_flag); cudaFree(d_cnt); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_tmp); };
+#define IL_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      set_error(ctx, std::string("ilu: " #call ": ") + cudaGetErrorString(e__));                   \
+      cleanup(); ilu_free(ctx);                                                                    \
+      return NSGPU_ECUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+  IL_CUDA(cudaMalloc(&d_flag, 2 * sizeof(int)));
+  IL_CUDA(cudaMalloc(&d_cnt, 65 * sizeof(unsigned long long)));
+  IL_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), s));
+  if (ctx->n_owned % 4 != 0 || nv <= 0 || nv > V.n_ent || nv >= (int64_t(1) << 31)) { P->unsupported = true; cleanup(); return NSGPU_OK; }
+  k_ilu_check<<<g256(nv), 256, 0, s>>>(nv, V.rowdof, d_flag);
+  int rc;
+  if ((rc = dev_alloc(ctx, &P->d_colour, nv)) || (rc = dev_alloc(ctx, &P->d_order, nv))) { cleanup(); ilu_free(ctx); return rc; }
+  IL_CUDA(cudaMemsetAsync(P->d_colour, 0xff, sizeof(int32_t) * nv, s));
+  int32_t* d_prev = reinterpret_cast<int32_t*>(P->d_order);   // round-start snapshot (the order array is filled later)
+  for (int round = 0; round < 1000; ++round) {
+    IL_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+    IL_CUDA(cudaMemcpyAsync(d_prev, P->d_colour, sizeof(int32_t) * nv, cudaMemcpyDeviceToDevice, s));
+    k_ilu_colour<<<g256(nv), 256, 0, s>>>(nv, ctx->n_owned, V.pair0, V.ns, ctx->d_pairs, d_prev, P->d_colour, d_cnt, d_flag + 1);
+    unsigned long long left = 0;
+    IL_CUDA(cudaMemcpyAsync(&left, d_cnt, sizeof(left), cudaMemcpyDeviceToHost, s));
+    IL_CUDA(cudaStreamSynchronize(s));
+    ctx->launches += 1;
+    if (left == 0) break;
+  }
+  int flags[2] = {0, 0};
+  IL_CUDA(cudaMemcpyAsync(flags, d_flag, sizeof(flags), cudaMemcpyDeviceToHost, s));
+  IL_CUDA(cudaStreamSynchronize(s));
+  if (flags[0] || flags[1]) { P->unsupported = true; cleanup(); return NSGPU_OK; }   // not the blocked numbering / more than 64 colours
+  IL_CUDA(cudaMalloc(&d_keys, sizeof(uint64_t) * nv));
+  IL_CUDA(cudaMalloc(&d_keys2, sizeof(uint64_t) * nv));
+  k_ilu_keys<<<g256(nv), 256, 0, s>>>(nv, P->d_colour, d_keys);
+  size_t tmp_bytes = 0;
+  IL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, nv, 0, 40, s));
+  IL_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+  IL_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys2, nv, 0, 40, s));
+  IL_CUDA(cudaMemsetAsync(d_cnt, 0, 65 * sizeof(unsigned long long), s));
+  k_ilu_order<<<g256(nv), 256, 0, s>>>(nv, d_keys2, P->d_order, d_cnt);
+  unsigned long long cnt[65];
+  IL_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  IL_CUDA(cudaStreamSynchronize(s));
+  IL_CUDA(cudaGetLastError());
+  ctx->launches += 3;
+  P->cstart.assign(1, 0);
+  for (int c = 0; c < 64; ++c) {
+    if (cnt[c] == 0) break;
+    P->cstart.push_back(P->cstart.back() + (int64_t)cnt[c]);
+  }
+  P->n_colours = (int)P->cstart.size() - 1;
+  if (P->cstart.back() != nv) { P->unsupported = true; cleanup(); return NSGPU_OK; }
+  if ((rc = dev_alloc(ctx, &P->d_lu, 16 * ctx->n_pairs)) || (rc = dev_alloc(ctx, &P->d_dinv, 16 * nv))) { cleanup(); ilu_free(ctx); return rc; }
+  cleanup();
+#undef IL_CUDA
+  return NSGPU_OK;
+}
+
+// factorise the Jacobian now resident in ctx->d_vals.  NSGPU_EUNSUPPORTED when the vertex-blocked view does not exist.
+int ilu_factor(nsgpu_ctx* ctx) {
+  P1BlockView V;
+  if (!p1tet_block_view(ctx, &V)) { set_error(ctx, "pc = ILU needs the vertex-blocked P1-P1 tet layout (block SpMV layout)"); return NSGPU_EUNSUPPORTED; }
+  IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
+  if (!P) {
+    const int rc = ilu_plan(ctx, V);
+    if (rc) return rc;
+    P = static_cast<IluPlan*>(ctx->ilu);
+  }
+  if (P->unsupported) { set_error(ctx, "pc = ILU: the numbering is not vertex-blocked or the vertex graph needs more than 64 colours"); return NSGPU_EUNSUPPORTED; }
+  cudaStream_t s = ctx->stream;
+  int* d_sing = nullptr;
+  NS_CUDA(ctx, cudaMalloc(&d_sing, sizeof(int)));
+  cudaMemsetAsync(d_sing, 0, sizeof(int), s);
+  k_ilu_load<<<g256(P->nv * 16), 256, 0, s>>>(P->nv, ctx->n_owned, V.pair0, V.ns, ctx->d_pairs, V.rowpos, ctx->d_vals, P->d_lu);
+  for (int c = 0; c < P->n_colours; ++c) {
+    const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
+    k_ilu_factor<<<(unsigned)ceil_div(i1 - i0, 64), 64, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu,
+                                                                   P->d_dinv, d_sing);
+  }
+  ctx->launches += 1 + P->n_colours;
+  int sing = 0;
+  cudaError_t e = cudaMemcpyAsync(&sing, d_sing, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d_sing);
+  if (e != cudaSuccess) { set_error(ctx, std::string("ilu factorisation: ") + cudaGetErrorString(e)); return NSGPU_ECUDA; }
+  if (sing) { set_error(ctx, "pc = ILU: a singular 4x4 pivot block (replaced by the identity)"); }   // not fatal: PETSc would shift; the block is skipped
+  return NSGPU_OK;
+}
+
+// d_z (owned entries) = U^-1 L^-1 d_r.  d_z may alias d_r.
+int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z) {
+  IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
+  P1BlockView V;
+  if (!P || P->unsupported || !P->d_lu || !p1tet_block_view(ctx, &V)) { set_error(ctx, "ilu_apply: no factorisation"); return NSGPU_EINVAL; }
+  cudaStream_t s = ctx->stream;
+  if (d_z != d_r) NS_CUDA(ctx, cudaMemcpyAsync(d_z, d_r, sizeof(double) * (size_t)ctx->n_owned, cudaMemcpyDeviceToDevice, s));
+  for (int c = 1; c < P->n_colours; ++c) {
+    const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
+    k_ilu_sweep<true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+  }
+  for (int c = P->n_colours - 1; c >= 0; --c) {
+    const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
+    k_ilu_sweep<false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+  }
+  ctx->launches += 2 * P->n_colours - 1;
+  NS_CUDA(ctx, cudaGetLastError());
+  return NSGPU_OK;
+}
+
+int ilu_colours(nsgpu_ctx* ctx, int32_t* h_colour, int32_t* n_colours) {
+  IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
+  if (!P || P->unsupported || !P->d_colour) { set_error(ctx, "ilu_colours: no factorisation"); return NSGPU_EINVAL; }
+  if (n_colours) *n_colours = P->n_colours;
+  if (h_colour) {
+    NS_CUDA(ctx, cudaMemcpyAsync(h_colour, P->d_colour, sizeof(int32_t) * (size_t)P->nv, cudaMemcpyDeviceToHost, ctx->stream));
+    NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NSGPU_OK;
+}
+
+}  // namespace nsgpu

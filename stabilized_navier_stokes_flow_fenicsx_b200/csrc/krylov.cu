@@ -278,11 +278,16 @@ static int reduce_and_update(nsgpu_ctx* ctx, Work& k, int nblocks, int what) {
 }
 
 // out (n_owned) = A M^-1 y
-static int apply_op(nsgpu_ctx* ctx, Work& k, int bs, const double* y, double* out) {
-  cudaStream_t s = ctx->stream;
-  k_pc_apply<<<(unsigned)ceil_div(k.n > 0 ? k.n : 1, 256), 256, 0, s>>>(k.n, bs, k.dinv, y, k.t);
+static int pc_apply(nsgpu_ctx* ctx, Work& k, int bs, const double* y, double* t) {
+  if (bs == 5) return ilu_apply(ctx, y, t);                       // multicolour block ILU(0), ilu.cu
+  k_pc_apply<<<(unsigned)ceil_div(k.n > 0 ? k.n : 1, 256), 256, 0, ctx->stream>>>(k.n, bs, k.dinv, y, t);
   ctx->launches += 1;
+  return NSGPU_OK;
+}
+
+static int apply_op(nsgpu_ctx* ctx, Work& k, int bs, const double* y, double* out) {
   int rc;
+  if ((rc = pc_apply(ctx, k, bs, y, k.t))) return rc;
   if ((rc = halo_forward(ctx, k.t))) return rc;
   return spmv_impl(ctx, k.t, out);
 }
@@ -302,8 +307,10 @@ int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, doub
   const unsigned g = vgrid(n);
   int bs = pc;
   if (bs == 4 && (n % 4 != 0 || ctx->gdim != 3 || ctx->vdeg != 1)) bs = 1;   // vertex blocks only exist for P1-P1 tets
-  if (bs != 0 && bs != 1 && bs != 4) { set_error(ctx, "tfqmr: pc must be 0 (none), 1 (Jacobi) or 4 (4x4 block Jacobi)"); return NSGPU_EINVAL; }
-  if (bs) {
+  if (bs != 0 && bs != 1 && bs != 4 && bs != 5) { set_error(ctx, "tfqmr: pc must be 0 (none), 1 (Jacobi), 4 (4x4 block Jacobi) or 5 (multicolour block ILU(0))"); return NSGPU_EINVAL; }
+  if (bs == 5) {
+    if ((rc = ilu_factor(ctx))) return rc;
+  } else if (bs) {
     const int64_t ne = bs == 4 ? n / 4 : n;
     k_pc_setup<<<(unsigned)ceil_div(ne > 0 ? ne : 1, 128), 128, 0, s>>>(n, bs, ctx->d_indptr, ctx->d_indices, ctx->d_diag, ctx->d_vals, k.dinv);
     ctx->launches += 1;
@@ -360,9 +367,9 @@ int tfqmr_impl(nsgpu_ctx* ctx, const double* d_b, double* d_x, double rtol, doub
     bound = h[S_BOUND];
   }
   // x = x0 + M^-1 yacc ; true residual norm for the caller
-  k_pc_apply<<<(unsigned)ceil_div(n > 0 ? n : 1, 256), 256, 0, s>>>(n, bs, k.dinv, k.yacc, k.t);
+  if ((rc = pc_apply(ctx, k, bs, k.yacc, k.t))) return rc;
   k_axpby<<<g, RED_THREADS, 0, s>>>(n, d_x, 1.0, k.t, d_x);
-  ctx->launches += 2;
+  ctx->launches += 1;
   if ((rc = halo_forward(ctx, d_x))) return rc;
   if ((rc = spmv_impl(ctx, d_x, k.u1))) return rc;
   k_axpby<<<g, RED_THREADS, 0, s>>>(n, d_b, -1.0, k.u1, k.u2);

@@ -150,6 +150,7 @@ int nsgpu_destroy(nsgpu_ctx* ctx) {
   cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_first); cudaFree(ctx->d_pair_last); cudaFree(ctx->d_members);
   p1tet_free(ctx);
   krylov_free(ctx);
+  ilu_free(ctx);
   rowown_free(ctx);
   trace_free(ctx);
   renumber_free(ctx);
@@ -560,6 +561,24 @@ int nsgpu_tfqmr(nsgpu_ctx* ctx, const double* b_owned, double* x_owned, double r
   if ((rc = vec_out(ctx, ctx->d_xvec, x_owned, ctx->n_owned))) return rc;
   NS_CUDA(ctx, cudaStreamSynchronize(s));
   return NSGPU_OK;
+}
+
+int nsgpu_ilu_apply(nsgpu_ctx* ctx, int refactor, const double* r_owned, double* z_owned) {
+  NS_ENTER(ctx);
+  NS_REQUIRE(ctx, ctx->pattern_built, "ilu_apply: call build_pattern and assemble a Jacobian first");
+  NS_REQUIRE(ctx, r_owned && z_owned, "ilu_apply: NULL argument");
+  int rc;
+  if ((refactor || !ctx->ilu) && (rc = ilu_factor(ctx))) return rc;
+  if ((rc = vec_in(ctx, r_owned, ctx->d_F, ctx->n_owned))) return rc;
+  if ((rc = ilu_apply(ctx, ctx->d_F, ctx->d_F))) return rc;
+  if ((rc = vec_out(ctx, ctx->d_F, z_owned, ctx->n_owned))) return rc;
+  NS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NSGPU_OK;
+}
+
+int nsgpu_ilu_colours(nsgpu_ctx* ctx, int32_t* colour, int32_t* n_colours) {
+  NS_ENTER(ctx);
+  return ilu_colours(ctx, colour, n_colours);
 }
 
 int nsgpu_axpy_dev(nsgpu_ctx* ctx, double a, const double* x_dev, double* y_dev) {

@@ -960,6 +960,14 @@ int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
   return 1;
 }
 
+bool p1tet_block_view(nsgpu_ctx* ctx, P1BlockView* out) {
+  if (!p1tet_fast_available(ctx)) return false;
+  nsgpu_p1tet_plan* P = ctx->p1plan;
+  if (!P || !P->contiguous || !ctx->d_pairs || P->n_ent == 0 || !P->d_ent_pair0 || !P->d_ent_ns) return false;
+  out->n_ent = P->n_ent; out->pair0 = P->d_ent_pair0; out->ns = P->d_ent_ns; out->rowpos = P->d_rowpos; out->rowdof = P->d_rowdof;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 void p1tet_free(nsgpu_ctx* ctx) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
