@@ -32,6 +32,17 @@ template <int GD> NS_HD double lam_of(const double* lam, int a) {
   return a == 0 ? lam[0] : (a == 1 ? lam[1] : lam[2]);
 }
 
+// The degree-2 rules (quad_point) have exactly one large barycentric coordinate per point: vertex q of the tetrahedron rule
+// (0.5854..., the others 0.1381...), vertex (0, 2, 1)[q] of the triangle rule (2/3, the others 1/6).  One compare and one select
+// replace the table.  (lam_0 = 1 - sum of the others in quad_point differs from these constants by at most an ulp.)
+template <int GD> struct QuadLam {
+  int kq;
+  NS_HD explicit QuadLam(int q) : kq(GD == 3 ? q : (q == 0 ? 0 : (q == 1 ? 2 : 1))) {}
+  NS_HD double operator()(int a) const {
+    return GD == 3 ? (a == kq ? 0.5854101966249685 : 0.1381966011250105) : (a == kq ? 2.0 / 3.0 : 1.0 / 6.0);
+  }
+};
+
 // Same quantities as point_setup (element_shared.cuh) without its basis / derivative tables: everything stays in registers.
 template <int GD, int VDEG>
 NS_HD void point_record(const FormParams& f, const double* x, const double* w, int q, double* rec, double* crec) {
@@ -129,8 +140,8 @@ struct NodeShape {
     if (VDEG == 1 || k <= GD) { a = b = k; kH = (VDEG == 2) ? 2.0 : 0.0; }
     else { edge_vertices<GD>(k - GD - 1, a, b); kH = 4.0; }
   }
-  NS_HD void eval(const double* lam, int k, double& N, double& ca, double& cb) const {
-    const double la = lam_of<GD>(lam, a), lb = lam_of<GD>(lam, b);
+  NS_HD void eval(const QuadLam<GD>& lam, int k, double& N, double& ca, double& cb) const {
+    const double la = lam(a), lb = lam(b);
     if (VDEG == 1) { N = la; ca = 1.0; cb = 0.0; }
     else {   // selects, not branches: the lanes of a group mix vertex and edge functions
       const bool v = k <= GD;
@@ -152,11 +163,11 @@ struct EntityBlock {
 
 // Block (m, n) of the element Jacobian (WANT_A) and the residual entry of row rsel of m (WANT_B; it shares the row-side
 // quantities of the block), all quadrature points.  recs: NQ point records (stride PREC), crec: cell record.
-template <int GD, int VDEG, bool WANT_A = true, bool WANT_B = false>
+template <int GD, int VDEG, bool WANT_A = true, bool WANT_B = false, int MV = -1 /* test entity: 1 vertex, 0 edge, -1 decided at run time */>
 NS_HD void entity_block(const FormParams& f, const double* recs, const double* crec, int m, int n, EntityBlock<GD>& o, int rsel = 0) {
   using T = ElemTraits<GD, VDEG>;
   constexpr int NV = GD + 1;
-  const bool m_vertex = m < NV, n_vertex = n < NV;
+  const bool m_vertex = MV < 0 ? m < NV : MV != 0, n_vertex = n < NV;
   for (int c = 0; c < GD; ++c) { o.pv[c] = 0.0; o.vp[c] = 0.0; for (int d = 0; d < GD; ++d) o.vv[c][d] = 0.0; }
   o.pp = 0.0; o.b = 0.0;
   NodeShape<GD, VDEG> Sm, Sn;
@@ -177,13 +188,12 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
 #pragma unroll 1
   for (int q = 0; q < T::NQ; ++q) {
     const double* R = recs + PREC * q;
-    double lam[NV], wt;
-    quad_point<GD>(q, lam, wt);
+    const QuadLam<GD> lam(q);
     const double W = R[PR_W];
     double Nm, cam, cbm, N, ca, cb, dNm[GD], dN[GD];
     Sm.eval(lam, m, Nm, cam, cbm);
     Sn.eval(lam, n, N, ca, cb);
-    const double lam_m = m_vertex ? lam_of<GD>(lam, m) : 0.0, lam_n = n_vertex ? lam_of<GD>(lam, n) : 0.0;
+    const double lam_m = m_vertex ? lam(m) : 0.0, lam_n = n_vertex ? lam(n) : 0.0;
     for (int j = 0; j < GD; ++j) { dNm[j] = cam * Am[j] + cbm * Bm[j]; dN[j] = ca * A[j] + cb * B[j]; }
     double dNdN = 0.0;
     for (int j = 0; j < GD; ++j) dNdN += dN[j] * dNm[j];
@@ -193,10 +203,10 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
       if (WANT_A) {
         for (int c = 0; c < GD; ++c) {
           o.vv[c][c] += W * f.alpha * dNdN;
-          if (n_vertex) o.vp[c] -= W * f.sp * lam_n * dNm[c];
+          o.vp[c] -= W * f.sp * lam_n * dNm[c];
           if (m_vertex) o.pv[c] += W * f.sp * lam_m * dN[c];
         }
-        if (m_vertex && n_vertex) o.pp += W * muT * glnglm;
+        if (m_vertex) o.pp += W * muT * glnglm;
       }
       if (WANT_B) {
         double br = 0.0;
@@ -258,7 +268,7 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
       const double s = Nm * udNn + f.nu * dNdN + tau * N * rdm;
       for (int c = 0; c < GD; ++c) {
         for (int d = 0; d < GD; ++d) o.vv[c][d] += W * (NmN * gu[c][d] + u[c] * Y[d] + dNm[c] * Z[d] + (c == d ? s : 0.0));
-        if (n_vertex) o.vp[c] += W * (tau * u[c] * glndNm - lam_n * dNm[c]);
+        o.vp[c] += W * (tau * u[c] * glndNm - lam_n * dNm[c]);
       }
       if (m_vertex) {
         for (int d = 0; d < GD; ++d) {
@@ -279,7 +289,7 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
           o.vv[c][d] += W * (gu[c][d] * k1 + (c == d ? s : 0.0) + rM[c] * N * (dtau[d] * udNm + tau * dNm[d]) - 0.5 * f.nu * tau * udNm * Hcd +
                              dNm[c] * Z[d]);
         }
-        if (n_vertex) o.vp[c] += W * (tau * gln[c] * udNm - lam_n * dNm[c]);
+        o.vp[c] += W * (tau * gln[c] * udNm - lam_n * dNm[c]);
       }
       if (m_vertex) {
         for (int d = 0; d < GD; ++d) {
@@ -291,7 +301,7 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
         }
       }
     }
-    if (m_vertex && n_vertex) o.pp += W * tau * glnglm;
+    if (m_vertex) o.pp += W * tau * glnglm;
   }
 }
 
@@ -309,13 +319,12 @@ NS_HD double entity_rhs(const FormParams& f, const double* recs, const double* c
 #pragma unroll 1
   for (int q = 0; q < T::NQ; ++q) {
     const double* R = recs + PREC * q;
-    double lam[NV], wt;
-    quad_point<GD>(q, lam, wt);
+    const QuadLam<GD> lam(q);
     const double W = R[PR_W], tau = R[PR_TAU], nuL = R[PR_NUL], divu = R[PR_DIVU], p = R[PR_P];
     if (r == GD) {   // pressure row
       double rT = 0.0, gpg = 0.0;
       for (int j = 0; j < GD; ++j) { rT += R[PR_RM + j] * glm[j]; gpg += R[PR_GP + j] * glm[j]; }
-      const double lam_m = lam_of<GD>(lam, m);
+      const double lam_m = lam(m);
       if (f.flavour == 2) b += W * (f.sp * lam_m * divu + f.beta * h * h * gpg);
       else b += W * (lam_m * divu + tau * rT);
       continue;

@@ -31,6 +31,7 @@ struct IluPlan {
   std::vector<int64_t> cstart;     // n_colours + 1 offsets into d_order
   double* d_lu = nullptr;          // 16 doubles per (vertex, neighbour) pair, row-major 4x4, indexed like ctx->d_pairs
   double* d_dinv = nullptr;        // 16 doubles per vertex: U_ii^-1
+  uint8_t* d_nbc = nullptr;        // per (vertex, neighbour) pair: colour of the neighbour (255: other rank's vertex, 254: the vertex itself)
   bool unsupported = false;
 };
 
@@ -82,6 +83,20 @@ __global__ void k_ilu_order(int64_t nv, const uint64_t* __restrict__ keys, int32
   if (i >= nv) return;
   order[i] = (int32_t)(keys[i] & 0xffffffffu);
   atomicAdd(count + (keys[i] >> 32), 1ull);
+}
+
+// neighbour colours next to the neighbour lists: the substitution sweeps read them in a stream instead of gathering colour[]
+__global__ void k_ilu_nbc(int64_t nv, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
+                          const uint64_t* __restrict__ pairs, const int32_t* __restrict__ colour, uint8_t* __restrict__ nbc) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t >> 4;
+  if (e >= nv) return;
+  const int64_t p0 = pair0[e];
+  const int n = ns[e];
+  for (int s = (int)(t & 15); s < n; s += 16) {
+    const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
+    nbc[p0 + s] = B >= n_owned ? 255 : ((B >> 2) == e ? 254 : (uint8_t)colour[B >> 2]);
+  }
 }
 
 // LU blocks <- the owned x owned blocks of the assembled Jacobian
@@ -242,7 +257,7 @@ k_ilu_factor(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __r
 // neighbours U_ij z_j)) substitution, in place.  Sixteen lanes per vertex, lane s takes neighbour s.
 template <bool LOWER>
 __global__ void __launch_bounds__(256)
-k_ilu_sweep(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __restrict__ order, const int32_t* __restrict__ colour,
+k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int32_t* __restrict__ order, const uint8_t* __restrict__ nbc,
             const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, const double* __restrict__ lu,
             const double* __restrict__ dinv, double* z) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -255,12 +270,9 @@ k_ilu_sweep(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __re
     const int64_t p0 = pair0[i];
     const int n = ns[i];
     for (int s = lane; s < n; s += 16) {
+      const int ck = nbc[p0 + s];
+      if (LOWER ? ck >= cc : (ck <= cc || ck >= 254)) continue;
       const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
-      if (B >= n_owned) continue;
-      const int64_t k = B >> 2;
-      if (k == i) continue;
-      const int ck = colour[k];
-      if (LOWER ? ck >= cc : ck <= cc) continue;
       const double* M = lu + 16 * (p0 + s);
       const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
 #pragma unroll
@@ -290,7 +302,7 @@ k_ilu_sweep(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __re
 void ilu_free(nsgpu_ctx* ctx) {
   IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
   if (!P) return;
-  cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv);
+  cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv); cudaFree(P->d_nbc);
   delete P;
   ctx->ilu = nullptr;
 }
@@ -363,7 +375,12 @@ static int ilu_plan(nsgpu_ctx* ctx, const P1BlockView& V) {
   }
   P->n_colours = (int)P->cstart.size() - 1;
   if (P->cstart.back() != nv) { P->unsupported = true; cleanup(); return NSGPU_OK; }
-  if ((rc = dev_alloc(ctx, &P->d_lu, 16 * ctx->n_pairs)) || (rc = dev_alloc(ctx, &P->d_dinv, 16 * nv))) { cleanup(); ilu_free(ctx); return rc; }
+  if ((rc = dev_alloc(ctx, &P->d_lu, 16 * ctx->n_pairs)) || (rc = dev_alloc(ctx, &P->d_dinv, 16 * nv)) || (rc = dev_alloc(ctx, &P->d_nbc, ctx->n_pairs))) {
+    cleanup(); ilu_free(ctx); return rc;
+  }
+  k_ilu_nbc<<<g256(nv * 16), 256, 0, s>>>(nv, ctx->n_owned, V.pair0, V.ns, ctx->d_pairs, P->d_colour, P->d_nbc);
+  ctx->launches += 1;
+  IL_CUDA(cudaGetLastError());
   cleanup();
 #undef IL_CUDA
   return NSGPU_OK;
@@ -410,11 +427,11 @@ int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z) {
   if (d_z != d_r) NS_CUDA(ctx, cudaMemcpyAsync(d_z, d_r, sizeof(double) * (size_t)ctx->n_owned, cudaMemcpyDeviceToDevice, s));
   for (int c = 1; c < P->n_colours; ++c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    k_ilu_sweep<true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    k_ilu_sweep<true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   for (int c = P->n_colours - 1; c >= 0; --c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    k_ilu_sweep<false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    k_ilu_sweep<false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   ctx->launches += 2 * P->n_colours - 1;
   NS_CUDA(ctx, cudaGetLastError());

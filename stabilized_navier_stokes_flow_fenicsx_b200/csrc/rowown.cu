@@ -247,7 +247,7 @@ k_rowown(RowOwnArgs a) {
             if (n < NV) op = rp[POFF + n];
           }
           EntityBlock<GD> B;
-          entity_block<GD, VDEG, true, WANT_F>(a.form, pr, cr, m, n, B, n);
+          entity_block<GD, VDEG, true, WANT_F, VCLASS ? 1 : 0>(a.form, pr, cr, m, n, B, n);
           if (WANT_F && n < R) brow += B.b;
           bool mk[GD], mkp = false;
 #pragma unroll
@@ -296,7 +296,7 @@ k_rowown(RowOwnArgs a) {
         }
         else if (WANT_F) {   // residual only, no constrained dof in the cell: the row-side part of the block routine
           EntityBlock<GD> B;
-          entity_block<GD, VDEG, false, true>(a.form, pr, cr, m, n < R ? n : 0, B, n);
+          entity_block<GD, VDEG, false, true, VCLASS ? 1 : 0>(a.form, pr, cr, m, n < R ? n : 0, B, n);
           if (n < R) brow += B.b;
         }
       }
