@@ -109,6 +109,7 @@ struct nsgpu_ctx {
   int kernel_sel = NSGPU_KERNEL_AUTO;
   int n_sms = 148;     // SM count of the device (nsgpu_create)
   int ws = 1;          // row-owner kernel: warp-specialised variant (two compute warpgroups + one gather warpgroup per SM) when it applies
+  bool rowown_lean = true;   // G-metric form on tetrahedra: row-side records + short mixed part (gm_row_side / gm_block) instead of entity_block
   int rowown = 1;      // atomics-free row-owner kernel (rowown.cu): 0 never (cooperative kernel with atomics), 1 for P2-P1 spaces, 2 for every space without a factorised kernel
   int pipe = 1;        // row-owner kernel: software-pipelined variant (all tile inputs arrive through cp.async, issued 1-2 tiles ahead)
   int fuse_fj = 0;     // nsgpu_residual also assembles J (one pass) and nsgpu_jacobian reuses it when called with the same state

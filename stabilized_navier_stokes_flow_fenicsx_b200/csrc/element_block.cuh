@@ -22,7 +22,8 @@ namespace nsgpu {
 constexpr int PREC = 32;   // doubles per (cell, point) record
 constexpr int CREC = 16;   // doubles per cell record
 // point record slots
-constexpr int PR_U = 0, PR_GU = 3, PR_RM = 12, PR_DTAU = 15, PR_DNUL = 18, PR_TAU = 21, PR_NUL = 22, PR_DIVU = 23, PR_W = 24, PR_P = 25, PR_GP = 26;
+constexpr int PR_U = 0, PR_GU = 3, PR_RM = 12, PR_DTAU = 15, PR_DNUL = 18, PR_TAU = 21, PR_NUL = 22, PR_DIVU = 23, PR_W = 24, PR_P = 25, PR_GP = 26,
+              PR_ZD = 29;   // div u * d nu_LSIC / d u (the lean G-metric blocks read the product)
 // cell record slots: gl[a][j] at 3 a + j, then
 constexpr int CR_H = 12;
 
@@ -120,6 +121,7 @@ NS_HD void point_record(const FormParams& f, const double* x, const double* w, i
     rec[PR_DTAU + i] = dtau[i];
     rec[PR_DNUL + i] = dnuL[i];
     rec[PR_GP + i] = gp[i];
+    rec[PR_ZD + i] = divu * dnuL[i];
   }
   rec[PR_TAU] = tau; rec[PR_NUL] = nuL; rec[PR_DIVU] = divu; rec[PR_W] = wt * g.scale; rec[PR_P] = p;
   if (crec) {
@@ -302,6 +304,142 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
       }
     }
     if (m_vertex) o.pp += W * tau * glnglm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lean G-metric blocks (flavour 0; NavierStokesChannelFlow.py:220-251): the point contribution to block (m, n) is split into
+// a ROW-SIDE record of (m, q) -- everything that does not depend on the trial entity, evaluated once per (cell, m, q) and
+// shared by the lanes of the row-owner group -- and a mixed part of ~90 instead of ~225 fp64 instructions per (m, n, q):
+//   W vv[c][d] = (N a0) gu[c][d] + u[c] (N aV[d] + k2 u[d] + h1 HXa[d] + h2 HXb[d]) + aD[c] (N ZD[d] + nuL dN[d]) + delta_cd s
+//   a0 = W Nm, a1 = W tau, a2 = W tau (rM . dNm), aV = W ((rM . dNm) dtau + tau gu dNm), aD = W dNm, h1|h2 = -nu W tau cam|cbm,
+//   k2 = tau (dN . aD), s = a0 (u . dN) + nu (dN . aD) + N a2;  HXa | HXb: the Hessian of N_n applied to the two gradient
+//   vectors dNm is a combination of (point independent, VDEG = 2 only).
+// The residual entries of m need the row side only: they leave gm_row_side with the record.
+constexpr int RSIDE = 16;   // doubles per (entity, point) row-side record
+constexpr int RS_A0 = 0, RS_A1 = 1, RS_A2 = 2, RS_H1 = 3, RS_H2 = 4, RS_WL = 5, RS_AV = 6, RS_AD = 9, RS_AP = 12;
+
+// MV: m is a vertex (pressure row).  b (nullable): GD (+ 1) residual contributions of this point, overwritten.
+template <int GD, int VDEG, bool MV>
+NS_HD void gm_row_side(const FormParams& f, const double* R, const double* crec, int m, int q, double* S, double* b) {
+  NodeShape<GD, VDEG> Sm;
+  Sm.init(m);
+  const QuadLam<GD> lam(q);
+  double Nm, cam, cbm, dNm[GD];
+  Sm.eval(lam, m, Nm, cam, cbm);
+  for (int j = 0; j < GD; ++j) dNm[j] = cam * crec[3 * Sm.a + j] + cbm * crec[3 * Sm.b + j];
+  const double W = R[PR_W], tau = R[PR_TAU];
+  double rdm = 0.0, gm[GD];
+  for (int j = 0; j < GD; ++j) rdm += R[PR_RM + j] * dNm[j];
+  for (int d = 0; d < GD; ++d) {
+    double g = 0.0;
+    for (int j = 0; j < GD; ++j) g += R[PR_GU + 3 * d + j] * dNm[j];
+    gm[d] = g;
+  }
+  const double Wt = W * tau, Wr = W * rdm, a0 = W * Nm, a2 = Wt * rdm;
+  S[RS_A0] = a0; S[RS_A1] = Wt; S[RS_A2] = a2; S[RS_H1] = -f.nu * Wt * cam; S[RS_H2] = -f.nu * Wt * cbm;
+  double aD[GD];
+  for (int d = 0; d < GD; ++d) {
+    S[RS_AV + d] = Wr * R[PR_DTAU + d] + Wt * gm[d];
+    aD[d] = W * dNm[d];
+    S[RS_AD + d] = aD[d];
+  }
+  double rTp = 0.0, wl = 0.0;
+  if (MV) {
+    double glm[GD];
+    for (int j = 0; j < GD; ++j) { glm[j] = crec[3 * m + j]; rTp += R[PR_RM + j] * glm[j]; }
+    wl = W * lam(m);
+    const double Wp = W * rTp;
+    for (int d = 0; d < GD; ++d) {
+      double g = 0.0;
+      for (int j = 0; j < GD; ++j) g += R[PR_GU + 3 * d + j] * glm[j];
+      S[RS_AP + d] = Wp * R[PR_DTAU + d] + Wt * g;
+    }
+  }
+  S[RS_WL] = wl;
+  if (b) {
+    const double divu = R[PR_DIVU], kk = R[PR_NUL] * divu - R[PR_P], nuW = f.nu * W;
+    for (int c = 0; c < GD; ++c) {
+      double conv = 0.0;
+      for (int j = 0; j < GD; ++j) conv += R[PR_U + j] * R[PR_GU + 3 * c + j];
+      b[c] = a0 * conv + aD[c] * kk + a2 * R[PR_U + c] + nuW * gm[c];
+    }
+    if (MV) b[GD] = wl * divu + Wt * rTp;
+  }
+}
+
+// block (m, n) from the NQ row-side records of m (rs, stride RSIDE) and the point records; o.b is not touched
+template <int GD, int VDEG, bool MV>
+NS_HD void gm_block(const FormParams& f, const double* recs, const double* crec, const double* rs, int m, int n, EntityBlock<GD>& o) {
+  using T = ElemTraits<GD, VDEG>;
+  constexpr int NV = GD + 1;
+  const bool n_vertex = n < NV;
+  NodeShape<GD, VDEG> Sm, Sn;
+  Sm.init(m); Sn.init(n);
+  double A[GD], B[GD], gln[GD], glm[GD], HXa[GD], HXb[GD], HXp[GD];
+  for (int j = 0; j < GD; ++j) {
+    A[j] = crec[3 * Sn.a + j]; B[j] = crec[3 * Sn.b + j];
+    gln[j] = n_vertex ? crec[3 * n + j] : 0.0;
+    glm[j] = MV ? crec[3 * m + j] : 0.0;
+    HXa[j] = HXb[j] = HXp[j] = 0.0;
+  }
+  double glnglm = 0.0;
+  for (int j = 0; j < GD; ++j) glnglm += gln[j] * glm[j];
+  if (VDEG == 2) {
+    double AB = 0.0, AAm = 0.0, BAm = 0.0, ABm = 0.0, BBm = 0.0, sAp = 0.0, sBp = 0.0;
+    for (int j = 0; j < GD; ++j) {
+      const double am = crec[3 * Sm.a + j], bm = crec[3 * Sm.b + j];
+      AB += A[j] * B[j];
+      AAm += A[j] * am; BAm += B[j] * am; ABm += A[j] * bm; BBm += B[j] * bm;
+      sAp += A[j] * glm[j]; sBp += B[j] * glm[j];
+    }
+    const double kH = Sn.kH, lap = 2.0 * kH * AB;
+    for (int d = 0; d < GD; ++d) {
+      HXa[d] = lap * crec[3 * Sm.a + d] + kH * (B[d] * AAm + A[d] * BAm);
+      HXb[d] = lap * crec[3 * Sm.b + d] + kH * (B[d] * ABm + A[d] * BBm);
+      if (MV) HXp[d] = lap * glm[d] + kH * (B[d] * sAp + A[d] * sBp);
+    }
+  }
+  for (int c = 0; c < GD; ++c) { o.pv[c] = 0.0; o.vp[c] = 0.0; for (int d = 0; d < GD; ++d) o.vv[c][d] = 0.0; }
+  o.pp = 0.0;
+  double tbar = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < T::NQ; ++q) {
+    const double* R = recs + PREC * q;
+    const double* S = rs + RSIDE * q;
+    const QuadLam<GD> lam(q);
+    double N, ca, cb, dN[GD], u[GD];
+    Sn.eval(lam, n, N, ca, cb);
+    const double lam_n = n_vertex ? lam(n) : 0.0;
+    double wdd = 0.0, udn = 0.0, wgl = 0.0, dgl = 0.0;
+    for (int j = 0; j < GD; ++j) {
+      dN[j] = ca * A[j] + cb * B[j];
+      u[j] = R[PR_U + j];
+      wdd += dN[j] * S[RS_AD + j]; udn += u[j] * dN[j]; wgl += gln[j] * S[RS_AD + j];
+      if (MV) dgl += dN[j] * glm[j];
+    }
+    const double tau = R[PR_TAU], nuL = R[PR_NUL], a0 = S[RS_A0], a1 = S[RS_A1];
+    const double k0 = N * a0, k2 = tau * wdd, kv = tau * wgl, kp = a1 * dgl;
+    const double s = a0 * udn + f.nu * wdd + N * S[RS_A2];
+    double t[GD], Zd[GD];
+    for (int d = 0; d < GD; ++d) {
+      double td = N * S[RS_AV + d] + k2 * u[d];
+      if (VDEG == 2) td += S[RS_H1] * HXa[d] + S[RS_H2] * HXb[d];
+      t[d] = td;
+      Zd[d] = N * R[PR_ZD + d] + nuL * dN[d];
+    }
+    for (int c = 0; c < GD; ++c) {
+      const double aDc = S[RS_AD + c];
+      for (int d = 0; d < GD; ++d) o.vv[c][d] += k0 * R[PR_GU + 3 * c + d] + u[c] * t[d] + aDc * Zd[d];
+      o.vv[c][c] += s;
+      o.vp[c] += kv * u[c] - lam_n * aDc;
+      if (MV) o.pv[c] += S[RS_WL] * dN[c] + N * S[RS_AP + c] + kp * u[c];
+    }
+    tbar += a1;
+  }
+  if (MV) {
+    if (VDEG == 2) for (int d = 0; d < GD; ++d) o.pv[d] -= f.nu * tbar * HXp[d];
+    o.pp = tbar * glnglm;
   }
 }
 

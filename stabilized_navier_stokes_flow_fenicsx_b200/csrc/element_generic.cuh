@@ -40,13 +40,13 @@ struct ElemTraits {
 };
 
 // basix reference-cell edge -> vertices
+// (tables {2,1,1,0,0,0} / {3,3,2,3,2,1} and {1,0,0} / {2,2,1} packed into nibbles: a run-time edge index then costs two shifts
+// instead of a local-memory array)
 template <int GD> NS_HD void edge_vertices(int e, int& a, int& b) {
   if (GD == 3) {
-    const int A[6] = {2, 1, 1, 0, 0, 0}, B[6] = {3, 3, 2, 3, 2, 1};
-    a = A[e]; b = B[e];
+    a = (0x000112 >> (4 * e)) & 15; b = (0x123233 >> (4 * e)) & 15;
   } else {
-    const int A[3] = {1, 0, 0}, B[3] = {2, 2, 1};
-    a = A[e]; b = B[e];
+    a = (0x001 >> (4 * e)) & 15; b = (0x122 >> (4 * e)) & 15;
   }
 }
 

@@ -127,6 +127,8 @@ k_ro_points(int64_t n_cells, FormParams form, const double* __restrict__ xg, con
   }
 }
 
+constexpr int RO_PAD = 4;   // doubles between the per-group copies of the staged records (bank spreading)
+
 struct RowOwnArgs {
   FormParams form;
   int64_t e0, e1;
@@ -152,14 +154,20 @@ __device__ __forceinline__ void ro_cp16(void* dst_shared, const void* src_global
 __device__ __forceinline__ void ro_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ro_cp_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-template <int GD, int VDEG, bool VCLASS, bool WANT_J, bool WANT_F>
-__global__ void __launch_bounds__(128, VDEG == 2 ? 3 : 4)
+// LEAN: the G-metric form through gm_row_side / gm_block (element_block.cuh): lanes 0 .. NQ-1 of a group evaluate the row-side
+// records of (entity, point) once per cell -- the residual entries come with them --, every lane then runs the short mixed part.
+template <int GD, int VDEG, bool VCLASS, bool WANT_J, bool WANT_F, bool LEAN>
+// (P2 vertex entities: the 4 x ~210 accumulator rows per group limit a CTA to two warps and an SM to ~8 warps, so the register budget can be 255)
+__global__ void __launch_bounds__(128, VDEG == 2 ? (VCLASS ? 2 : 3) : 4)
 k_rowown(RowOwnArgs a) {
   using T = ElemTraits<GD, VDEG>;
   constexpr int NENT = T::NENT, ND = T::ND, NV = GD + 1, NQ = T::NQ, POFF = T::POFF;
   constexpr int GPW = 32 / NENT;               // groups per warp
   constexpr int R = VCLASS ? GD + 1 : GD;      // rows of the entity
   constexpr int STG = NQ * PREC + CREC;        // doubles of one staged cell: its point records and its cell record
+  // the lanes of a group read the same staged word (broadcast), the groups of a warp their own copies: 4 doubles of padding per
+  // group put the three copies into different 16-byte bank groups (unpadded strides are multiples of 128 bytes: 3-way conflicts)
+  constexpr int STGP = 2 * STG + RO_PAD, RSP = NQ * RSIDE + RO_PAD;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gw = lane / NENT, n = lane - gw * NENT;
@@ -168,8 +176,10 @@ k_rowown(RowOwnArgs a) {
   const int g = warp * GPW + (active ? gw : 0);
   double* acc = smem + (size_t)g * R * a.lstride;
   double* red = smem + (size_t)G * R * a.lstride + (size_t)g * NENT * 4;
-  double* stage = smem + (size_t)G * R * a.lstride + (size_t)G * NENT * 4 + (size_t)g * 2 * STG;   // double buffer of the group
+  double* stage = smem + (size_t)G * R * a.lstride + (size_t)G * NENT * 4 + (size_t)g * STGP;   // double buffer of the group
+  double* rsd = smem + (size_t)G * R * a.lstride + (size_t)G * NENT * 4 + (size_t)G * STGP + (size_t)g * RSP;   // row-side records (LEAN)
   const unsigned FULL = 0xffffffffu;
+  const unsigned gmask = active ? (((1u << NENT) - 1u) << (gw * NENT)) : 0u;
   // the group's lanes copy the records of one cell (16-byte pieces, cp.async) into stage buffer b
   auto fetch = [&](int64_t cell, int b) {
     double* dst = stage + b * STG;
@@ -210,6 +220,9 @@ k_rowown(RowOwnArgs a) {
 #pragma unroll
     for (int r = 0; r < R; ++r) lift[r] = 0.0;
     double brow = 0.0;
+    double brow4[R];          // LEAN: residual contributions of this lane's quadrature point, all rows of the entity
+#pragma unroll
+    for (int r = 0; r < R; ++r) brow4[r] = 0.0;
 
     // the entity's incidence words: up to 3 NENT of them live in the group's registers and are handed round by shuffle
     uint32_t iw0 = 0, iw1 = 0, iw2 = 0;
@@ -237,6 +250,17 @@ k_rowown(RowOwnArgs a) {
         const double* pr = stage + (it & 1) * STG;
         const double* cr = pr + NQ * PREC;
         const bool cbc = a.marker && a.cellbc[cell];
+        if (LEAN) {
+          if (n < NQ) {
+            double bq[R];
+            gm_row_side<GD, VDEG, VCLASS>(a.form, pr + PREC * n, cr, m, n, rsd + RSIDE * n, WANT_F ? bq : nullptr);
+            if (WANT_F) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) brow4[r] += bq[r];
+            }
+          }
+          __syncwarp(gmask);
+        }
         if (WANT_J || cbc) {
           const int32_t* dm = a.dofmap + cell * ND;
           const uint16_t* rp = a.rel + (cell * NENT + m) * ND;
@@ -247,8 +271,11 @@ k_rowown(RowOwnArgs a) {
             if (n < NV) op = rp[POFF + n];
           }
           EntityBlock<GD> B;
-          entity_block<GD, VDEG, true, WANT_F, VCLASS ? 1 : 0>(a.form, pr, cr, m, n, B, n);
-          if (WANT_F && n < R) brow += B.b;
+          if (LEAN) gm_block<GD, VDEG, VCLASS>(a.form, pr, cr, rsd, m, n, B);
+          else {
+            entity_block<GD, VDEG, true, WANT_F, VCLASS ? 1 : 0>(a.form, pr, cr, m, n, B, n);
+            if (WANT_F && n < R) brow += B.b;
+          }
           bool mk[GD], mkp = false;
 #pragma unroll
           for (int d = 0; d < GD; ++d) mk[d] = false;
@@ -294,7 +321,7 @@ k_rowown(RowOwnArgs a) {
             }
           }
         }
-        else if (WANT_F) {   // residual only, no constrained dof in the cell: the row-side part of the block routine
+        else if (WANT_F && !LEAN) {   // residual only, no constrained dof in the cell: the row-side part of the block routine
           EntityBlock<GD> B;
           entity_block<GD, VDEG, false, true, VCLASS ? 1 : 0>(a.form, pr, cr, m, n < R ? n : 0, B, n);
           if (n < R) brow += B.b;
@@ -306,7 +333,7 @@ k_rowown(RowOwnArgs a) {
     if (WANT_F) {
       if (has) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) red[n * 4 + r] = lift[r] + (n == r ? brow : 0.0);
+        for (int r = 0; r < R; ++r) red[n * 4 + r] = lift[r] + (LEAN ? (n < NQ ? brow4[r] : 0.0) : (n == r ? brow : 0.0));
       }
       __syncwarp();
       if (has && n < R) {
@@ -417,7 +444,8 @@ static int rowown_build(nsgpu_ctx* ctx) {
 
 // shared memory of a launch: accumulator rows + reduction scratch per group
 static size_t ro_smem(int groups, int rows, int lstride, int nent, int nq) {
-  return sizeof(double) * ((size_t)groups * rows * lstride + (size_t)groups * nent * 4 + (size_t)groups * 2 * (nq * PREC + CREC));
+  return sizeof(double) * ((size_t)groups * rows * lstride + (size_t)groups * nent * 4 + (size_t)groups * (2 * (nq * PREC + CREC) + RO_PAD) +
+                           (size_t)groups * (nq * RSIDE + RO_PAD));
 }
 
 template <int GD, int VDEG, bool VCLASS>
@@ -436,16 +464,25 @@ static int rowown_launch_class(nsgpu_ctx* ctx, RowOwnPlan* P, RowOwnArgs a, bool
   const int64_t need = ceil_div(P->n_ent[cls], G);
   const int64_t cap = (int64_t)ctx->n_sms * 16;
   const unsigned grid = (unsigned)(need < cap ? need : cap);
-#define RO_LAUNCH(J, F)                                                                                                              \
-  do {                                                                                                                               \
-    if (smem > 48 * 1024)                                                                                                            \
-      NS_CUDA(ctx, cudaFuncSetAttribute(k_rowown<GD, VDEG, VCLASS, J, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    k_rowown<GD, VDEG, VCLASS, J, F><<<grid, warps * 32, smem, ctx->stream>>>(a);                                                    \
+  // the lean G-metric path is compiled for tetrahedra (the reference's G-metric form lives on the 3-D channel / duct meshes)
+  constexpr bool CAN_LEAN = GD == 3;
+  const bool lean = CAN_LEAN && a.form.flavour == NSGPU_FORM_GMETRIC && ctx->rowown_lean;
+#define RO_LAUNCH1(J, F, L)                                                                                                              \
+  do {                                                                                                                                  \
+    if (smem > 48 * 1024)                                                                                                               \
+      NS_CUDA(ctx, cudaFuncSetAttribute(k_rowown<GD, VDEG, VCLASS, J, F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k_rowown<GD, VDEG, VCLASS, J, F, L><<<grid, warps * 32, smem, ctx->stream>>>(a);                                                    \
+  } while (0)
+#define RO_LAUNCH(J, F)                                  \
+  do {                                                   \
+    if (lean) RO_LAUNCH1(J, F, CAN_LEAN);                \
+    else RO_LAUNCH1(J, F, false);                        \
   } while (0)
   if (want_J && want_F) RO_LAUNCH(true, true);
   else if (want_J) RO_LAUNCH(true, false);
   else RO_LAUNCH(false, true);
 #undef RO_LAUNCH
+#undef RO_LAUNCH1
   ctx->launches += 1;
   return NSGPU_OK;
 }

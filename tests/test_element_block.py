@@ -49,3 +49,8 @@ def test_blocks_equal_rows(host, gd, vdeg, form):
         scale = np.abs(Ar).max()
         assert np.abs(Ab - Ar).max() <= 2e-13 * scale, (gd, vdeg, form, np.abs(Ab - Ar).max() / scale)
         assert np.abs(bb - br).max() <= 2e-13 * max(np.abs(br).max(), 1e-30)
+        if form[0] == 0:   # the lean G-metric blocks (row-side records + mixed part), the row-owner kernel's flavour-0 path
+            Al, bl = np.empty((nd, nd)), np.empty(nd)
+            assert host.lean_blocks(gd, vdeg, ctypes.c_double(form[1]), ctypes.c_double(form[2]), _p(x), _p(w), _p(Al), _p(bl)) == 0
+            assert np.abs(Al - Ar).max() <= 2e-13 * scale, (gd, vdeg, form, np.abs(Al - Ar).max() / scale)
+            assert np.abs(bl - br).max() <= 2e-13 * max(np.abs(br).max(), 1e-30)
