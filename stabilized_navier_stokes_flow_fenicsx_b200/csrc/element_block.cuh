@@ -166,7 +166,8 @@ struct EntityBlock {
 // Block (m, n) of the element Jacobian (WANT_A) and the residual entry of row rsel of m (WANT_B; it shares the row-side
 // quantities of the block), all quadrature points.  recs: NQ point records (stride PREC), crec: cell record.
 template <int GD, int VDEG, bool WANT_A = true, bool WANT_B = false, int MV = -1 /* test entity: 1 vertex, 0 edge, -1 decided at run time */>
-NS_HD void entity_block(const FormParams& f, const double* recs, const double* crec, int m, int n, EntityBlock<GD>& o, int rsel = 0) {
+NS_HD void entity_block(const FormParams& f, const double* recs, const double* crec, int m, int n, EntityBlock<GD>& o, int rsel = 0,
+                         int rstride = PREC /* doubles between the point records (the kernel pads them in shared memory) */) {
   using T = ElemTraits<GD, VDEG>;
   constexpr int NV = GD + 1;
   const bool m_vertex = MV < 0 ? m < NV : MV != 0, n_vertex = n < NV;
@@ -189,7 +190,7 @@ NS_HD void entity_block(const FormParams& f, const double* recs, const double* c
 
 #pragma unroll 1
   for (int q = 0; q < T::NQ; ++q) {
-    const double* R = recs + PREC * q;
+    const double* R = recs + rstride * q;
     const QuadLam<GD> lam(q);
     const double W = R[PR_W];
     double Nm, cam, cbm, N, ca, cb, dNm[GD], dN[GD];
@@ -370,7 +371,8 @@ NS_HD void gm_row_side(const FormParams& f, const double* R, const double* crec,
 
 // block (m, n) from the NQ row-side records of m (rs, stride RSIDE) and the point records; o.b is not touched
 template <int GD, int VDEG, bool MV>
-NS_HD void gm_block(const FormParams& f, const double* recs, const double* crec, const double* rs, int m, int n, EntityBlock<GD>& o) {
+NS_HD void gm_block(const FormParams& f, const double* recs, const double* crec, const double* rs, int m, int n, EntityBlock<GD>& o,
+                     int rstride = PREC, int sstride = RSIDE /* doubles between the point / row-side records */) {
   using T = ElemTraits<GD, VDEG>;
   constexpr int NV = GD + 1;
   const bool n_vertex = n < NV;
@@ -405,8 +407,8 @@ NS_HD void gm_block(const FormParams& f, const double* recs, const double* crec,
   double tbar = 0.0;
 #pragma unroll 1
   for (int q = 0; q < T::NQ; ++q) {
-    const double* R = recs + PREC * q;
-    const double* S = rs + RSIDE * q;
+    const double* R = recs + rstride * q;
+    const double* S = rs + sstride * q;
     const QuadLam<GD> lam(q);
     double N, ca, cb, dN[GD], u[GD];
     Sn.eval(lam, n, N, ca, cb);

@@ -128,6 +128,7 @@ k_ro_points(int64_t n_cells, FormParams form, const double* __restrict__ xg, con
 }
 
 constexpr int RO_PAD = 4;   // doubles between the per-group copies of the staged records (bank spreading)
+constexpr int RO_RPAD = 2;  // doubles between consecutive point / row-side records of a group: lanes 0 .. NQ-1 read record q = lane in the row-side phase
 
 struct RowOwnArgs {
   FormParams form;
@@ -164,10 +165,11 @@ k_rowown(RowOwnArgs a) {
   constexpr int NENT = T::NENT, ND = T::ND, NV = GD + 1, NQ = T::NQ, POFF = T::POFF;
   constexpr int GPW = 32 / NENT;               // groups per warp
   constexpr int R = VCLASS ? GD + 1 : GD;      // rows of the entity
-  constexpr int STG = NQ * PREC + CREC;        // doubles of one staged cell: its point records and its cell record
+  constexpr int SREC = PREC + RO_RPAD, SRS = RSIDE + RO_RPAD;   // record strides in shared memory (lane q of a group works on record q)
+  constexpr int STG = NQ * SREC + CREC;        // doubles of one staged cell: its point records and its cell record
   // the lanes of a group read the same staged word (broadcast), the groups of a warp their own copies: 4 doubles of padding per
   // group put the three copies into different 16-byte bank groups (unpadded strides are multiples of 128 bytes: 3-way conflicts)
-  constexpr int STGP = 2 * STG + RO_PAD, RSP = NQ * RSIDE + RO_PAD;
+  constexpr int STGP = 2 * STG + RO_PAD, RSP = NQ * SRS + RO_PAD;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gw = lane / NENT, n = lane - gw * NENT;
@@ -185,9 +187,10 @@ k_rowown(RowOwnArgs a) {
     double* dst = stage + b * STG;
     const double* pr = a.prec + cell * (NQ * PREC);
     const double* cr = a.crec + cell * CREC;
-    for (int k = n; k < STG / 2; k += NENT) {
-      const double* src = k < NQ * PREC / 2 ? pr + 2 * k : cr + 2 * (k - NQ * PREC / 2);
-      ro_cp16(dst + 2 * k, src);
+    for (int k = n; k < (NQ * PREC + CREC) / 2; k += NENT) {
+      const bool rec = k < NQ * PREC / 2;
+      const double* src = rec ? pr + 2 * k : cr + 2 * (k - NQ * PREC / 2);
+      ro_cp16(dst + 2 * k + (rec ? (k / (PREC / 2)) * RO_RPAD : NQ * RO_RPAD), src);
     }
   };
 
@@ -214,8 +217,12 @@ k_rowown(RowOwnArgs a) {
     const int maxcnt = __reduce_max_sync(FULL, cnt);
     const int maxL = __reduce_max_sync(FULL, L);
     bool rmk[R];
+    int64_t rstart[R];       // CSR starts of the entity's rows: asked for now, needed when the last cell is done
 #pragma unroll
-    for (int r = 0; r < R; ++r) rmk[r] = (has && a.marker) ? a.marker[gi[r]] != 0 : false;
+    for (int r = 0; r < R; ++r) {
+      rmk[r] = (has && a.marker) ? a.marker[gi[r]] != 0 : false;
+      rstart[r] = (WANT_J && has) ? a.indptr[gi[r]] : 0;
+    }
     double lift[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) lift[r] = 0.0;
@@ -248,12 +255,12 @@ k_rowown(RowOwnArgs a) {
         const int64_t cell = wd >> 4;
         const int m = (int)(wd & 15u);
         const double* pr = stage + (it & 1) * STG;
-        const double* cr = pr + NQ * PREC;
+        const double* cr = pr + NQ * SREC;
         const bool cbc = a.marker && a.cellbc[cell];
         if (LEAN) {
           if (n < NQ) {
             double bq[R];
-            gm_row_side<GD, VDEG, VCLASS>(a.form, pr + PREC * n, cr, m, n, rsd + RSIDE * n, WANT_F ? bq : nullptr);
+            gm_row_side<GD, VDEG, VCLASS>(a.form, pr + SREC * n, cr, m, n, rsd + SRS * n, WANT_F ? bq : nullptr);
             if (WANT_F) {
 #pragma unroll
               for (int r = 0; r < R; ++r) brow4[r] += bq[r];
@@ -271,9 +278,9 @@ k_rowown(RowOwnArgs a) {
             if (n < NV) op = rp[POFF + n];
           }
           EntityBlock<GD> B;
-          if (LEAN) gm_block<GD, VDEG, VCLASS>(a.form, pr, cr, rsd, m, n, B);
+          if (LEAN) gm_block<GD, VDEG, VCLASS>(a.form, pr, cr, rsd, m, n, B, SREC, SRS);
           else {
-            entity_block<GD, VDEG, true, WANT_F, VCLASS ? 1 : 0>(a.form, pr, cr, m, n, B, n);
+            entity_block<GD, VDEG, true, WANT_F, VCLASS ? 1 : 0>(a.form, pr, cr, m, n, B, n, SREC);
             if (WANT_F && n < R) brow += B.b;
           }
           bool mk[GD], mkp = false;
@@ -303,27 +310,36 @@ k_rowown(RowOwnArgs a) {
             }
           }
           if (WANT_J) {
+            // The (row, column) positions of one lane are pairwise distinct, and so are the columns of different lanes: all loads of a
+            // batch are issued before its first store (written as read-modify-writes one after the other the compiler has to keep
+            // every load behind the previous store: 16 dependent shared-memory round trips per cell).
+            double old[R][GD];
+#pragma unroll
+            for (int d = 0; d < GD; ++d)
+#pragma unroll
+              for (int r = 0; r < R; ++r) old[r][d] = acc[r * a.lstride + ov[d]];
 #pragma unroll
             for (int d = 0; d < GD; ++d) {
               if (mk[d]) continue;
-              const int o = ov[d];
 #pragma unroll
               for (int c = 0; c < GD; ++c)
-                if (!rmk[c]) acc[c * a.lstride + o] += B.vv[c][d];
-              if (VCLASS && !rmk[R - 1]) acc[(R - 1) * a.lstride + o] += B.pv[d];
+                if (!rmk[c]) acc[c * a.lstride + ov[d]] = old[c][d] + B.vv[c][d];
+              if (VCLASS && !rmk[R - 1]) acc[(R - 1) * a.lstride + ov[d]] = old[R - 1][d] + B.pv[d];
             }
             if (n < NV && !mkp) {
-              const int o = op;
+              double oldp[R];
+#pragma unroll
+              for (int r = 0; r < R; ++r) oldp[r] = acc[r * a.lstride + op];
 #pragma unroll
               for (int c = 0; c < GD; ++c)
-                if (!rmk[c]) acc[c * a.lstride + o] += B.vp[c];
-              if (VCLASS && !rmk[R - 1]) acc[(R - 1) * a.lstride + o] += B.pp;
+                if (!rmk[c]) acc[c * a.lstride + op] = oldp[c] + B.vp[c];
+              if (VCLASS && !rmk[R - 1]) acc[(R - 1) * a.lstride + op] = oldp[R - 1] + B.pp;
             }
           }
         }
         else if (WANT_F && !LEAN) {   // residual only, no constrained dof in the cell: the row-side part of the block routine
           EntityBlock<GD> B;
-          entity_block<GD, VDEG, false, true, VCLASS ? 1 : 0>(a.form, pr, cr, m, n < R ? n : 0, B, n);
+          entity_block<GD, VDEG, false, true, VCLASS ? 1 : 0>(a.form, pr, cr, m, n < R ? n : 0, B, n, SREC);
           if (n < R) brow += B.b;
         }
       }
@@ -351,7 +367,7 @@ k_rowown(RowOwnArgs a) {
         if (k < L) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            a.vals[a.indptr[gi[r]] + k] = acc[r * a.lstride + k];
+            a.vals[rstart[r] + k] = acc[r * a.lstride + k];
             acc[r * a.lstride + k] = 0.0;
           }
         }
@@ -444,8 +460,8 @@ static int rowown_build(nsgpu_ctx* ctx) {
 
 // shared memory of a launch: accumulator rows + reduction scratch per group
 static size_t ro_smem(int groups, int rows, int lstride, int nent, int nq) {
-  return sizeof(double) * ((size_t)groups * rows * lstride + (size_t)groups * nent * 4 + (size_t)groups * (2 * (nq * PREC + CREC) + RO_PAD) +
-                           (size_t)groups * (nq * RSIDE + RO_PAD));
+  return sizeof(double) * ((size_t)groups * rows * lstride + (size_t)groups * nent * 4 + (size_t)groups * (2 * (nq * (PREC + RO_RPAD) + CREC) + RO_PAD) +
+                           (size_t)groups * (nq * (RSIDE + RO_RPAD) + RO_PAD));
 }
 
 template <int GD, int VDEG, bool VCLASS>
