@@ -28,8 +28,7 @@ struct RowOwnPlan {
   uint32_t* d_inc = nullptr;        // incidences (cell << 4 | local entity), grouped by entity
   int4* d_ent_hdr = nullptr;        // per entity two int4 (vertex entities first; inside a class by falling incidence count, so that the
                                     //  groups of a warp walk equally many cells): {first incidence lo, hi, incidences, row length}, {row dofs}
-  double* d_prec = nullptr;         // [cell][point][PREC]
-  double* d_crec = nullptr;         // [cell][CREC]
+  double* d_prec = nullptr;         // [cell][NQ point records of PREC doubles | cell record of CREC doubles]: one contiguous piece per cell
   uint8_t* d_cellbc = nullptr;      // cell holds a constrained dof
   bool unsupported = false;
   bool attr_set = false;
@@ -98,8 +97,7 @@ __global__ void k_ro_perm(int64_t n_ent, const uint64_t* __restrict__ key2, cons
 template <int GD, int VDEG>
 __global__ void __launch_bounds__(128)
 k_ro_points(int64_t n_cells, FormParams form, const double* __restrict__ xg, const int32_t* __restrict__ cells, const int32_t* __restrict__ dofmap,
-            const double* __restrict__ wv, const uint8_t* __restrict__ marker, double* __restrict__ prec, double* __restrict__ crec,
-            uint8_t* __restrict__ cellbc) {
+            const double* __restrict__ wv, const uint8_t* __restrict__ marker, double* __restrict__ prec, uint8_t* __restrict__ cellbc) {
   using T = ElemTraits<GD, VDEG>;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_cells * T::NQ) return;
@@ -118,10 +116,10 @@ k_ro_points(int64_t n_cells, FormParams form, const double* __restrict__ xg, con
   }
   double rec[PREC], cr[CREC];
   point_record<GD, VDEG>(form, x, w, q, rec, cr);
-  double* o = prec + (cell * T::NQ + q) * PREC;
+  double* o = prec + cell * (T::NQ * PREC + CREC) + q * PREC;
   for (int k = 0; k < PREC; ++k) o[k] = rec[k];
   if (q == 0) {
-    double* oc = crec + cell * CREC;
+    double* oc = prec + cell * (T::NQ * PREC + CREC) + T::NQ * PREC;
     for (int k = 0; k < CREC; ++k) oc[k] = cr[k];
     cellbc[cell] = bc ? 1 : 0;
   }
@@ -138,8 +136,7 @@ struct RowOwnArgs {
   const int32_t* dofmap;
   const uint16_t* rel;
   const int64_t* indptr;
-  const double* prec;
-  const double* crec;
+  const double* prec;       // per cell: NQ point records, then the cell record
   const uint8_t* cellbc;
   const uint8_t* marker;     // nullptr without Dirichlet conditions
   const double* bc_value;
@@ -185,12 +182,11 @@ k_rowown(RowOwnArgs a) {
   // the group's lanes copy the records of one cell (16-byte pieces, cp.async) into stage buffer b
   auto fetch = [&](int64_t cell, int b) {
     double* dst = stage + b * STG;
-    const double* pr = a.prec + cell * (NQ * PREC);
-    const double* cr = a.crec + cell * CREC;
-    for (int k = n; k < (NQ * PREC + CREC) / 2; k += NENT) {
-      const bool rec = k < NQ * PREC / 2;
-      const double* src = rec ? pr + 2 * k : cr + 2 * (k - NQ * PREC / 2);
-      ro_cp16(dst + 2 * k + (rec ? (k / (PREC / 2)) * RO_RPAD : NQ * RO_RPAD), src);
+    const double* src = a.prec + cell * (NQ * PREC + CREC);
+#pragma unroll
+    for (int j = 0; j < ((NQ * PREC + CREC) / 2 + NENT - 1) / NENT; ++j) {
+      const int k = n + j * NENT;                      // 16-byte piece k of the cell's records; record k / (PREC / 2) is shifted by its padding
+      if (k < (NQ * PREC + CREC) / 2) ro_cp16(dst + 2 * k + min(k / (PREC / 2), NQ) * RO_RPAD, src + 2 * k);
     }
   };
 
@@ -380,7 +376,7 @@ k_rowown(RowOwnArgs a) {
 void rowown_free(nsgpu_ctx* ctx) {
   RowOwnPlan* P = static_cast<RowOwnPlan*>(ctx->rowown_plan);
   if (!P) return;
-  cudaFree(P->d_inc); cudaFree(P->d_ent_hdr); cudaFree(P->d_prec); cudaFree(P->d_crec); cudaFree(P->d_cellbc);
+  cudaFree(P->d_inc); cudaFree(P->d_ent_hdr); cudaFree(P->d_prec); cudaFree(P->d_cellbc);
   delete P;
   ctx->rowown_plan = nullptr;
 }
@@ -435,8 +431,8 @@ static int rowown_build(nsgpu_ctx* ctx) {
   RO_CUDA(cudaMalloc(&d_start, sizeof(int64_t) * (n_ent + 1)));
   RO_CUDA(cudaMalloc(&d_k2, sizeof(uint64_t) * n_ent));
   RO_CUDA(cudaMalloc(&d_k2s, sizeof(uint64_t) * n_ent));
-  if ((rc = dev_alloc(ctx, &P->d_ent_hdr, 2 * n_ent)) || (rc = dev_alloc(ctx, &P->d_inc, n)) || (rc = dev_alloc(ctx, &P->d_prec, nc * T::NQ * PREC)) ||
-      (rc = dev_alloc(ctx, &P->d_crec, nc * CREC)) || (rc = dev_alloc(ctx, &P->d_cellbc, nc))) { cleanup(); rowown_free(ctx); return rc; }
+  if ((rc = dev_alloc(ctx, &P->d_ent_hdr, 2 * n_ent)) || (rc = dev_alloc(ctx, &P->d_inc, n)) || (rc = dev_alloc(ctx, &P->d_prec, nc * (T::NQ * PREC + CREC))) ||
+      (rc = dev_alloc(ctx, &P->d_cellbc, nc))) { cleanup(); rowown_free(ctx); return rc; }
   k_ro_scatter<<<(unsigned)ceil_div(n + 1, 256), 256, 0, s>>>(n, d_keys2, d_head, d_pos, ctx->d_indptr, d_start, P->d_inc, d_cnt, d_lmax);
   k_ro_key2<<<(unsigned)ceil_div(n_ent, 256), 256, 0, s>>>(n_ent, d_start, d_keys2, d_k2);
   cudaFree(d_tmp); d_tmp = nullptr;
@@ -473,8 +469,15 @@ static int rowown_launch_class(nsgpu_ctx* ctx, RowOwnPlan* P, RowOwnArgs a, bool
   a.e0 = VCLASS ? 0 : P->n_ent[0];
   a.e1 = a.e0 + P->n_ent[cls];
   a.lstride = want_J ? (P->lmax[cls] + 3) & ~3 : 0;
-  int warps = 4;
-  while (warps > 1 && ro_smem(warps * GPW, R, a.lstride, T::NENT, T::NQ) > 110 * 1024) warps >>= 1;
+  // warps per CTA: the choice that keeps most warps resident on an SM (227 KB of shared memory; the P2 vertex class is shared-memory
+  // bound: ~30 KB per warp of accumulator rows and staged records)
+  int warps = 4, best = 0;
+  for (int w = 4; w >= 1; w >>= 1) {
+    const size_t need = ro_smem(w * GPW, R, a.lstride, T::NENT, T::NQ) + 1024;
+    const int regcap = VDEG == 2 ? (VCLASS ? 8 : 12) : 16;          // warps the register file holds at the launch bounds of k_rowown
+    const int resident = std::min((int)std::min<size_t>(227 * 1024 / need, 32) * w, regcap);
+    if (resident > best) { best = resident; warps = w; }           // ties: the larger CTA
+  }
   const size_t smem = ro_smem(warps * GPW, R, a.lstride, T::NENT, T::NQ);
   const int G = warps * GPW;
   const int64_t need = ceil_div(P->n_ent[cls], G);
@@ -510,13 +513,13 @@ static int rowown_run(nsgpu_ctx* ctx, const double* d_xin, bool want_J, bool wan
   const int64_t nc = ctx->n_cells_owned;
   const uint8_t* mk = ctx->has_bc ? ctx->d_bc_marker : nullptr;
   k_ro_points<GD, VDEG><<<(unsigned)ceil_div(nc * T::NQ, 128), 128, 0, ctx->stream>>>(nc, ctx->form, ctx->d_x, ctx->d_cells, ctx->d_dofmap, d_xin, mk,
-                                                                                      P->d_prec, P->d_crec, P->d_cellbc);
+                                                                                      P->d_prec, P->d_cellbc);
   ctx->launches += 1;
   RowOwnArgs a;
   a.form = ctx->form;
   a.e0 = a.e1 = 0;
   a.ent_hdr = P->d_ent_hdr; a.inc = P->d_inc; a.dofmap = ctx->d_dofmap; a.rel = ctx->d_rel; a.indptr = ctx->d_indptr;
-  a.prec = P->d_prec; a.crec = P->d_crec; a.cellbc = P->d_cellbc; a.marker = mk; a.bc_value = ctx->d_bc_value; a.wv = d_xin;
+  a.prec = P->d_prec; a.cellbc = P->d_cellbc; a.marker = mk; a.bc_value = ctx->d_bc_value; a.wv = d_xin;
   a.vals = ctx->d_vals; a.F = d_Fout; a.lstride = 0;
   int rc = rowown_launch_class<GD, VDEG, true>(ctx, P, a, want_J, want_F);
   if (rc == NSGPU_OK && VDEG == 2) rc = rowown_launch_class<GD, VDEG, false>(ctx, P, a, want_J, want_F);
