@@ -74,7 +74,7 @@ def main():
         a = agg[fl]
         a["inst"] += f(r, "Instructions Executed")
         a["samples"] += f(r, "# Samples")
-        for k in ("stall_short_sb", "stall_long_sb", "stall_wait", "stall_branch_resolving", "stall_mio", "stall_math"):
+        for k in ("stall_short_sb", "stall_long_sb", "stall_wait", "stall_branch_resolving", "stall_mio", "stall_math", "stall_barrier", "stall_selected", "stall_not_selected"):
             a[k] += f(r, k)
         a["wave"] += f(r, "L1 Wavefronts Shared")
         a["wave_x"] += f(r, "L1 Wavefronts Shared Excessive")
@@ -82,10 +82,10 @@ def main():
     for a in agg.values():
         tot.update(a)
     print(f"total: {tot['inst']:.0f} warp-instructions, {tot['samples']:.0f} samples, shared wavefronts {tot['wave']:.0f} (excessive {tot['wave_x']:.0f})")
-    print(f"{'file:line':28s} {'inst%':>6s} {'smp%':>6s} {'ssb':>6s} {'lsb':>6s} {'wait':>6s} {'wave%':>6s} {'excess%':>7s}")
+    print(f"{'file:line':28s} {'inst%':>6s} {'smp%':>6s} {'ssb':>6s} {'lsb':>6s} {'wait':>6s} {'bar':>6s} {'issue':>6s} {'wave%':>6s} {'excess%':>7s}")
     for fl, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
         print(f"{fl[0] + ':' + str(fl[1]):28s} {100 * a['inst'] / tot['inst']:6.2f} {100 * a['samples'] / tot['samples']:6.2f} {a['stall_short_sb']:6.0f} {a['stall_long_sb']:6.0f} "
-              f"{a['stall_wait']:6.0f} {100 * a['wave'] / max(tot['wave'], 1):6.2f} {100 * a['wave_x'] / max(tot['wave_x'], 1):7.2f}")
+              f"{a['stall_wait']:6.0f} {a['stall_barrier']:6.0f} {a['stall_selected']:6.0f} {100 * a['wave'] / max(tot['wave'], 1):6.2f} {100 * a['wave_x'] / max(tot['wave_x'], 1):7.2f}")
     # by file
     byfile = collections.defaultdict(lambda: collections.Counter())
     for fl, a in agg.items():
