@@ -65,6 +65,7 @@ struct nsgpu_p1tet_plan {
   uint8_t* d_tile_bytes = nullptr;  // per tile: slot-list offsets | vertex of each slot | diagonal slot of each vertex (16-B padded segments)
   int64_t* d_ent_pair0 = nullptr;   // [n_ent] first entry of the vertex's neighbour list in ctx->d_pairs
   int32_t* d_ent_ns = nullptr;      // [n_ent] number of neighbours (4x4 blocks per row)
+  uint32_t* d_colb = nullptr;       // [n_pairs] first dof of the column vertex of every block (block SpMV with 256-bit loads)
   bool contiguous = false;          // every vertex's dofs are (first dof) + 0,1,2,3 and first dof is even
   // warp-specialised kernel (p1tet_ws.cuh): per-tile blobs fetched with bulk copies
   uint8_t* d_cblob = nullptr;       // [n_tiles][WS_CBLOB] distinct-vertex list | vertex positions | cell words
@@ -901,10 +902,23 @@ static inline unsigned g256(int64_t n);
 // column index per block, taken from the entity pair list of the pattern build, instead of 16 int32 column indices.
 // Sixteen lanes per vertex; lane s owns neighbour s: one 32-byte load of x[B], four 32-byte loads of values (one per row,
 // contiguous across lanes), 16 FMAs; the four row sums are reduced over the lanes with shuffles.
-template <int MINB>
+// WIDE: rows and x are 32-byte aligned: one 256-bit load per row piece / x block (sm_100: LDG.E.256) instead of two 128-bit ones that ask
+// for every 32-byte sector twice; the column of a block comes from a 4-byte list (colb) instead of the 8-byte pair words.
+__device__ __forceinline__ double4 ld256_stream(const double* p) {
+  double4 r;
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld256_nc(const double* p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
+template <int MINB, bool WIDE>
 __global__ void __launch_bounds__(256, MINB)
 k_spmv_block4(int64_t n_ent, int64_t n_owned, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns,
-              const uint64_t* __restrict__ pairs, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
+              const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ colb, const int64_t* __restrict__ rowpos, const int4* __restrict__ rowdof,
               const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t e = t >> 4;
@@ -920,14 +934,24 @@ k_spmv_block4(int64_t n_ent, int64_t n_owned, const int64_t* __restrict__ pair0,
       const longlong2 r01 = rp[0], r23 = rp[1];
       const int64_t rpos[4] = {r01.x, r01.y, r23.x, r23.y};
       for (int s = lane; s < n; s += 16) {
-        const uint32_t B = (uint32_t)(pairs[p0 + s] & 0xffffffffu);
-        const double2* xp = reinterpret_cast<const double2*>(x + B);
-        const double2 xa = __ldg(xp), xb = __ldg(xp + 1);
+        if (WIDE) {
+          const uint32_t B = colb[p0 + s];
+          const double4 xv = ld256_nc(x + B);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double2* vp = reinterpret_cast<const double2*>(vals + rpos[c] + 4 * s);
-          const double2 va = __ldcs(vp), vb = __ldcs(vp + 1);
-          acc[c] += va.x * xa.x + va.y * xa.y + vb.x * xb.x + vb.y * xb.y;
+          for (int c = 0; c < 4; ++c) {
+            const double4 v = ld256_stream(vals + rpos[c] + 4 * s);
+            acc[c] += v.x * xv.x + v.y * xv.y + v.z * xv.z + v.w * xv.w;
+          }
+        } else {
+          const uint32_t B = (uint32_t)(pairs[p0 + s] & 0xffffffffu);
+          const double2* xp = reinterpret_cast<const double2*>(x + B);
+          const double2 xa = __ldg(xp), xb = __ldg(xp + 1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double2* vp = reinterpret_cast<const double2*>(vals + rpos[c] + 4 * s);
+            const double2 va = __ldcs(vp), vb = __ldcs(vp + 1);
+            acc[c] += va.x * xa.x + va.y * xa.y + vb.x * xb.x + vb.y * xb.y;
+          }
         }
       }
     }
@@ -942,6 +966,11 @@ k_spmv_block4(int64_t n_ent, int64_t n_owned, const int64_t* __restrict__ pair0,
   }
 }
 
+__global__ void k_pair_cols(int64_t n, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ colb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) colb[i] = (uint32_t)(pairs[i] & 0xffffffffu);
+}
+
 // returns 1 when the block kernel ran, 0 when the caller should use the plain CSR kernel
 int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
   nsgpu_p1tet_plan* P = ctx->p1plan;
@@ -952,10 +981,20 @@ int p1tet_spmv(nsgpu_ctx* ctx, const double* d_x, double* d_y) {
       if (ctx->colx_leader[k] + ctx->colx_slot[k] != (int64_t)ctx->n_dofs + (int64_t)k || ctx->colx_size[k] != 4 || ctx->colx_leader[k] % 4 != 0) P->colx_ok = 0;
   }
   if (!P->colx_ok) return 0;
-#define SPMV_B4(MB) k_spmv_block4<MB><<<g256(P->n_ent * 16), 256, 0, ctx->stream>>>(P->n_ent, ctx->n_owned, P->d_ent_pair0, P->d_ent_ns, ctx->d_pairs, \
-      P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof), ctx->d_vals, d_x, d_y)
+  // 256-bit loads need 32-byte aligned rows (plan flag) and vectors (x holds whole vertex blocks; the base pointer is the caller's)
+  const bool wide = ctx->spmv_wide && P->rows32 && (reinterpret_cast<uintptr_t>(d_x) & 31) == 0 && (reinterpret_cast<uintptr_t>(ctx->d_vals) & 31) == 0;
+  if (wide && !P->d_colb) {   // 4-byte block columns beside the pair words, built on first use
+    if (cudaMalloc(&P->d_colb, sizeof(uint32_t) * (size_t)(ctx->n_pairs > 0 ? ctx->n_pairs : 1)) != cudaSuccess) { cudaGetLastError(); P->d_colb = nullptr; }
+    else {
+      k_pair_cols<<<g256(ctx->n_pairs), 256, 0, ctx->stream>>>(ctx->n_pairs, ctx->d_pairs, P->d_colb);
+      ctx->launches += 1;
+    }
+  }
+#define SPMV_B4(MB, W) k_spmv_block4<MB, W><<<g256(P->n_ent * 16), 256, 0, ctx->stream>>>(P->n_ent, ctx->n_owned, P->d_ent_pair0, P->d_ent_ns, ctx->d_pairs, \
+      P->d_colb, P->d_rowpos, reinterpret_cast<const int4*>(P->d_rowdof), ctx->d_vals, d_x, d_y)
   // resident CTAs per SM the kernel is compiled for (register budget 56 / 48 / 40): option "spmv_blocks"
-  if (ctx->spmv_blocks >= 6) SPMV_B4(6); else if (ctx->spmv_blocks == 5) SPMV_B4(5); else SPMV_B4(4);
+  if (wide && P->d_colb) { if (ctx->spmv_blocks >= 6) SPMV_B4(6, true); else if (ctx->spmv_blocks == 5) SPMV_B4(5, true); else SPMV_B4(4, true); }
+  else { if (ctx->spmv_blocks >= 6) SPMV_B4(6, false); else if (ctx->spmv_blocks == 5) SPMV_B4(5, false); else SPMV_B4(4, false); }
 #undef SPMV_B4
   return 1;
 }
@@ -974,7 +1013,7 @@ void p1tet_free(nsgpu_ctx* ctx) {
   if (!P) return;
   cudaFree(P->d_tile_vlist); cudaFree(P->d_inc_loc); cudaFree(P->d_inc_cell); cudaFree(P->d_inc_vtx); cudaFree(P->d_inc_lead); cudaFree(P->d_src); cudaFree(P->d_ent_rel);
   cudaFree(P->d_cblob); cudaFree(P->d_hblob); cudaFree(P->d_hword);
-  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns);
+  cudaFree(P->d_rowpos); cudaFree(P->d_rowdof); cudaFree(P->d_tile_hdr); cudaFree(P->d_tile_bytes); cudaFree(P->d_ent_pair0); cudaFree(P->d_ent_ns); cudaFree(P->d_colb);
   if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
   if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
   for (cudaEvent_t e : P->ev_h2d) cudaEventDestroy(e);
