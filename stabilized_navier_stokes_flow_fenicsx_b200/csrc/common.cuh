@@ -229,4 +229,23 @@ int import_values(nsgpu_ctx* ctx, double* d_src_caller);
 int caller_vals_buffer(nsgpu_ctx* ctx);
 int translate_positions(nsgpu_ctx* ctx, int64_t n, const int64_t* h_pos_caller, int64_t* d_pos_internal);
 
+#ifdef __CUDACC__
+// 256-bit global loads (sm_100: LDG.E.256; the address must be 32-byte aligned): streaming (evict-first), read-only path, plain
+__device__ __forceinline__ double4 ld256_stream(const double* p) {
+  double4 r;
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld256_nc(const double* p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld256(const double* p) {
+  double4 r;
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+  return r;
+}
+#endif
+
 }  // namespace nsgpu

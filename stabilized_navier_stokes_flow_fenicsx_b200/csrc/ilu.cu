@@ -255,7 +255,7 @@ k_ilu_factor(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __r
 
 // one colour of the forward (LOWER: z_i -= sum over earlier neighbours L_ik z_k) or backward (z_i = U_ii^-1 (z_i - sum over later
 // neighbours U_ij z_j)) substitution, in place.  Sixteen lanes per vertex, lane s takes neighbour s.
-template <bool LOWER>
+template <bool LOWER, bool WIDE>
 __global__ void __launch_bounds__(256)
 k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int32_t* __restrict__ order, const uint8_t* __restrict__ nbc,
             const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, const double* __restrict__ lu,
@@ -274,9 +274,18 @@ k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int32_t* __restrict__ order, c
       if (LOWER ? ck >= cc : (ck <= cc || ck >= 254)) continue;
       const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
       const double* M = lu + 16 * (p0 + s);
-      const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
+      if (WIDE) {   // one 256-bit load per block row and for the four z entries of the neighbour (other colours: not written by this launch)
+        const double4 zz = ld256(z + B);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += M[4 * r] * z0 + M[4 * r + 1] * z1 + M[4 * r + 2] * z2 + M[4 * r + 3] * z3;
+        for (int r = 0; r < 4; ++r) {
+          const double4 m = ld256_stream(M + 4 * r);
+          acc[r] += m.x * zz.x + m.y * zz.y + m.z * zz.z + m.w * zz.w;
+        }
+      } else {
+        const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] += M[4 * r] * z0 + M[4 * r + 1] * z1 + M[4 * r + 2] * z2 + M[4 * r + 3] * z3;
+      }
     }
   }
 #pragma unroll
@@ -425,13 +434,16 @@ int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z) {
   if (!P || P->unsupported || !P->d_lu || !p1tet_block_view(ctx, &V)) { set_error(ctx, "ilu_apply: no factorisation"); return NSGPU_EINVAL; }
   cudaStream_t s = ctx->stream;
   if (d_z != d_r) NS_CUDA(ctx, cudaMemcpyAsync(d_z, d_r, sizeof(double) * (size_t)ctx->n_owned, cudaMemcpyDeviceToDevice, s));
+  const bool wide = (reinterpret_cast<uintptr_t>(d_z) & 31) == 0 && (reinterpret_cast<uintptr_t>(P->d_lu) & 31) == 0;   // 256-bit loads
   for (int c = 1; c < P->n_colours; ++c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    k_ilu_sweep<true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    if (wide) k_ilu_sweep<true, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    else k_ilu_sweep<true, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   for (int c = P->n_colours - 1; c >= 0; --c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    k_ilu_sweep<false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    if (wide) k_ilu_sweep<false, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    else k_ilu_sweep<false, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   ctx->launches += 2 * P->n_colours - 1;
   NS_CUDA(ctx, cudaGetLastError());

@@ -210,7 +210,7 @@ __global__ void k_pc_setup(int64_t n, int bs, const int64_t* __restrict__ indptr
 }
 
 // t = M^-1 y (owned entries; ghosts are refreshed by the halo before the product)
-__global__ void k_pc_apply(int64_t n, int bs, const double* __restrict__ dinv, const double* __restrict__ y, double* __restrict__ t) {
+__global__ void k_pc_apply(int64_t n, int bs, const double* __restrict__ dinv, const double* __restrict__ y, double* __restrict__ t, bool wide) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (bs == 0) { t[i] = y[i]; return; }
@@ -219,6 +219,11 @@ __global__ void k_pc_apply(int64_t n, int bs, const double* __restrict__ dinv, c
   const int r = (int)(i & 3);
   const double* D = dinv + 16 * e + 4 * r;
   const double* yy = y + 4 * e;
+  if (wide) {   // 32-byte aligned vectors: one 256-bit load each
+    const double4 d = ld256_nc(D), v = ld256_nc(yy);
+    t[i] = d.x * v.x + d.y * v.y + d.z * v.z + d.w * v.w;
+    return;
+  }
   t[i] = D[0] * yy[0] + D[1] * yy[1] + D[2] * yy[2] + D[3] * yy[3];
 }
 
@@ -280,7 +285,8 @@ static int reduce_and_update(nsgpu_ctx* ctx, Work& k, int nblocks, int what) {
 // out (n_owned) = A M^-1 y
 static int pc_apply(nsgpu_ctx* ctx, Work& k, int bs, const double* y, double* t) {
   if (bs == 5) return ilu_apply(ctx, y, t);                       // multicolour block ILU(0), ilu.cu
-  k_pc_apply<<<(unsigned)ceil_div(k.n > 0 ? k.n : 1, 256), 256, 0, ctx->stream>>>(k.n, bs, k.dinv, y, t);
+  const bool wide = bs == 4 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(k.dinv)) & 31) == 0;
+  k_pc_apply<<<(unsigned)ceil_div(k.n > 0 ? k.n : 1, 256), 256, 0, ctx->stream>>>(k.n, bs, k.dinv, y, t, wide);
   ctx->launches += 1;
   return NSGPU_OK;
 }

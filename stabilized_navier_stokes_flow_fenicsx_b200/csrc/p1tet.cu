@@ -904,16 +904,6 @@ static inline unsigned g256(int64_t n);
 // contiguous across lanes), 16 FMAs; the four row sums are reduced over the lanes with shuffles.
 // WIDE: rows and x are 32-byte aligned: one 256-bit load per row piece / x block (sm_100: LDG.E.256) instead of two 128-bit ones that ask
 // for every 32-byte sector twice; the column of a block comes from a 4-byte list (colb) instead of the 8-byte pair words.
-__device__ __forceinline__ double4 ld256_stream(const double* p) {
-  double4 r;
-  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ double4 ld256_nc(const double* p) {
-  double4 r;
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
 
 template <int MINB, bool WIDE>
 __global__ void __launch_bounds__(256, MINB)
