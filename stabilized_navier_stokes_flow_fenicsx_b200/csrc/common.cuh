@@ -132,7 +132,9 @@ struct nsgpu_ctx {
   const char* last_kernel = "none";   // which assembly variant the last call used (nsgpu_last_kernel_name)
 
   // multi-GPU
-  int overlap = 1;          // option: ghost-row tiles first, then their exchanges run on a second stream beside the interior tiles
+  int overlap = 0;          // option: ghost-row tiles first, then their exchanges run on a second stream beside the interior tiles.
+                            // Off by default: measured on L the split costs more than the hidden exchange saves (2 GPUs 13.4 vs 12.3 ms per
+                            // step, 8 GPUs 3.47 vs 3.48 ms) -- the NCCL kernels hold SMs the persistent assembly CTAs then queue behind
   int sm_reserve = 4;       // SMs the interior launch leaves to the exchange kernels (a persistent grid would starve them otherwise)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_x[2] = {nullptr, nullptr};
