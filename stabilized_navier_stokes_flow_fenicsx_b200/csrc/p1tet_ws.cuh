@@ -309,13 +309,21 @@ __device__ __forceinline__ void ws_gather(const unsigned char* __restrict__ H, c
       if (j < n_off) {
         const unsigned char* rec = H + 32 + 16 * nent + 32 * j;
         const int4 sr = *reinterpret_cast<const int4*>(rec);           // len | ovf << 16, out_off, rowlen
-        const uint16_t* lst = reinterpret_cast<const uint16_t*>(rec + 16);
+        const uint4 lw = *reinterpret_cast<const uint4*>(rec + 16);      // the eight inline list entries in one load (no per-entry index reads)
         const int len = sr.x & 0xffff, n0 = len < WS_LIST ? len : WS_LIST;
         double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
-#pragma unroll 2
-        for (int q = 0; q < n0; ++q) {
-          const double2 a0 = base[lst[q]], a1 = base[lst[q] + WS_SS];
-          acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+#pragma unroll
+        for (int q2 = 0; q2 < WS_LIST / 2; ++q2) {
+          if (2 * q2 < n0) {
+            const uint32_t w = q2 == 0 ? lw.x : (q2 == 1 ? lw.y : (q2 == 2 ? lw.z : lw.w));
+            const uint32_t i0 = w & 0xffffu;
+            const double2 a0 = base[i0], a1 = base[i0 + WS_SS];
+            acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+            if (2 * q2 + 1 < n0) {
+              const double2 b0 = base[w >> 16], b1 = base[(w >> 16) + WS_SS];
+              acc.x += b0.x; acc.y += b0.y; acc.z += b1.x; acc.w += b1.y;
+            }
+          }
         }
         if (len > WS_LIST) {   // rare: an edge shared by more than eight cells
           const uint16_t* ov = reinterpret_cast<const uint16_t*>(H + 32 + 16 * nent + 32 * n_off) + ((unsigned)sr.x >> 16);
