@@ -476,7 +476,7 @@ static int rowown_launch_class(nsgpu_ctx* ctx, RowOwnPlan* P, RowOwnArgs a, bool
     const size_t need = ro_smem(w * GPW, R, a.lstride, T::NENT, T::NQ) + 1024;
     const int regcap = VDEG == 2 ? (VCLASS ? 8 : 12) : 16;          // warps the register file holds at the launch bounds of k_rowown
     const int resident = std::min((int)std::min<size_t>(227 * 1024 / need, 32) * w, regcap);
-    if (resident > best) { best = resident; warps = w; }           // ties: the larger CTA
+    if (4 * resident > 5 * best) { best = resident; warps = w; }   // a smaller CTA only for >= 25 % more resident warps (measured: near-ties favour the larger CTA)
   }
   const size_t smem = ro_smem(warps * GPW, R, a.lstride, T::NENT, T::NQ);
   const int G = warps * GPW;
