@@ -115,6 +115,43 @@ def test_rowowner_kernel_writes_every_entry_once_and_is_reproducible(oracle, kin
     asm.close()
 
 
+def test_lean_and_unsplit_rowowner_blocks_agree(oracle):
+    """P2-P1 G-metric tets: the lean blocks (row-side records + mixed part, the default) and the unsplit entity_block formulation
+    (option rowown_lean = 0) give the same Jacobian and residual to rounding, with the state off the Dirichlet values (lifting active)."""
+    m, sp, w, bcs, fk = _case("duct_p2")
+    w = w + 0.01 * np.random.default_rng(11).standard_normal(sp.n_dofs)
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix()
+    v1, F1 = asm.jacobian_residual(w)
+    assert asm.last_kernel_name() == "rowown"
+    Fr = asm.residual(w)                                   # residual-only pass of the lean path (row side only)
+    assert np.abs(Fr - F1).max() <= 1e-13 * np.abs(F1).max()
+    asm.set_option("rowown_lean", 0)
+    v0, F0 = asm.jacobian_residual(w)
+    assert np.abs(v1 - v0).max() <= RTOL * np.abs(v0).max() and np.abs(F1 - F0).max() <= RTOL * np.abs(F0).max()
+    if oracle is not None:
+        indptr, indices, vals, F = _oracle_all(oracle, m, sp, w, bcs, fk)
+        assert np.abs(v1 - vals).max() <= RTOL * np.abs(vals).max() and np.abs(F1 - F).max() <= RTOL * np.abs(F).max()
+    asm.close()
+
+
+def test_wide_and_narrow_block_spmv_agree():
+    """The vertex-blocked SpMV with 256-bit loads and the 4-byte block-column list (default) against the same kernel with 128-bit
+    loads and the pair words (option spmv_wide = 0): the same sums in the same order (1e-14: the compiler may contract differently)."""
+    m, sp, w, bcs, fk = _case("duct_p1")
+    asm = _gpu(m, sp, bcs, fk)
+    asm.create_matrix()
+    asm.jacobian_residual(w)
+    x = np.random.default_rng(5).standard_normal(sp.n_dofs)
+    y1 = asm.mult(x)
+    assert asm.last_spmv_name() == "spmv_block4"
+    asm.set_option("spmv_wide", 0)
+    y0 = asm.mult(x)
+    assert asm.last_spmv_name() == "spmv_block4"
+    assert np.abs(y0 - y1).max() <= 1e-14 * np.abs(y0).max()
+    asm.close()
+
+
 @pytest.mark.parametrize("kernel,ws,pipe,expect", [(1, 0, 0, "generic_row"), (2, 1, 1, "p1tet_ws"), (2, 0, 1, "p1tet_pipe"), (2, 0, 0, "p1tet_tiles")])
 def test_generic_and_fast_kernels_agree(oracle, kernel, ws, pipe, expect):
     """kernel 1 = generic (thread per cell row, atomics); kernel 2 = factorised row-owner kernels, which must apply:
