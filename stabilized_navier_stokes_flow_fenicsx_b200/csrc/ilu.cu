@@ -28,6 +28,7 @@ struct IluPlan {
   int n_colours = 0;
   int32_t* d_colour = nullptr;     // per owned vertex
   int32_t* d_order = nullptr;      // vertices sorted by (colour, vertex)
+  int4* d_orec = nullptr;          // per position of the order: (vertex, neighbours, first pair lo, hi): one load instead of order -> pair0 / ns
   std::vector<int64_t> cstart;     // n_colours + 1 offsets into d_order
   double* d_lu = nullptr;          // 16 doubles per (vertex, neighbour) pair, row-major 4x4, indexed like ctx->d_pairs
   double* d_dinv = nullptr;        // 16 doubles per vertex: U_ii^-1
@@ -97,6 +98,15 @@ __global__ void k_ilu_nbc(int64_t nv, int64_t n_owned, const int64_t* __restrict
     const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
     nbc[p0 + s] = B >= n_owned ? 255 : ((B >> 2) == e ? 254 : (uint8_t)colour[B >> 2]);
   }
+}
+
+// the sweeps' per-vertex record in elimination order
+__global__ void k_ilu_orec(int64_t nv, const int32_t* __restrict__ order, const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, int4* __restrict__ orec) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  const int32_t i = order[idx];
+  const int64_t p0 = pair0[i];
+  orec[idx] = make_int4(i, ns[i], (int)(p0 & 0xffffffffLL), (int)(p0 >> 32));
 }
 
 // LU blocks <- the owned x owned blocks of the assembled Jacobian
@@ -254,38 +264,69 @@ k_ilu_factor(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __r
 }
 
 // one colour of the forward (LOWER: z_i -= sum over earlier neighbours L_ik z_k) or backward (z_i = U_ii^-1 (z_i - sum over later
-// neighbours U_ij z_j)) substitution, in place.  Sixteen lanes per vertex, lane s takes neighbour s.
+// neighbours U_ij z_j)) substitution, in place.  Sixteen lanes per vertex.
+// WIDE (32-byte aligned factor and vector): four lanes per block -- lane (slot, r) loads row r of the block of neighbour slot, slot + 4, ...
+// with one 256-bit load, so that one load instruction of the four lanes asks for the whole 128-byte block at once -- and the row
+// sums are reduced over the four slots.  Otherwise: lane s takes neighbour s with scalar loads.
 template <bool LOWER, bool WIDE>
 __global__ void __launch_bounds__(256)
-k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int32_t* __restrict__ order, const uint8_t* __restrict__ nbc,
-            const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, const double* __restrict__ lu,
-            const double* __restrict__ dinv, double* z) {
+k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int4* __restrict__ orec, const uint8_t* __restrict__ nbc,
+            const uint64_t* __restrict__ pairs, const double* __restrict__ lu, const double* __restrict__ dinv, double* z) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t idx = i0 + (t >> 4);
   const int lane = (int)(t & 15);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   int64_t i = 0;
+  if (WIDE) {
+    const int r = lane & 3, slot = lane >> 2;
+    double acc = 0.0;
+    if (idx < i1) {
+      const int4 rec = orec[idx];
+      i = rec.x;
+      const int n = rec.y;
+      const int64_t p0 = (int64_t)(uint32_t)rec.z | ((int64_t)rec.w << 32);
+#pragma unroll 2
+      for (int s = slot; s < n; s += 4) {
+        const int ck = nbc[p0 + s];
+        const uint64_t pw = pairs[p0 + s];          // asked for together with the colour byte: one memory round trip less on the chain
+        if (LOWER ? ck >= cc : (ck <= cc || ck >= 254)) continue;
+        const int64_t B = (int64_t)(pw & 0xffffffffu);
+        const double4 m = ld256_stream(lu + 16 * (p0 + s) + 4 * r);
+        const double4 zz = ld256(z + B);
+        acc += m.x * zz.x + m.y * zz.y + m.z * zz.z + m.w * zz.w;
+      }
+    }
+    acc += __shfl_down_sync(0xffffffffu, acc, 8, 16);
+    acc += __shfl_down_sync(0xffffffffu, acc, 4, 16);
+    // lanes 0..3 of the group hold the row sums; y = z_i - sums
+    double y = 0.0;
+    if (idx < i1 && slot == 0) y = z[4 * i + r] - acc;
+    if (LOWER) {
+      if (idx < i1 && slot == 0) z[4 * i + r] = y;
+    } else {
+      const double y0 = __shfl_sync(0xffffffffu, y, 0, 16), y1 = __shfl_sync(0xffffffffu, y, 1, 16);
+      const double y2 = __shfl_sync(0xffffffffu, y, 2, 16), y3 = __shfl_sync(0xffffffffu, y, 3, 16);
+      if (idx < i1 && slot == 0) {
+        const double4 d = ld256_nc(dinv + 16 * i + 4 * r);
+        z[4 * i + r] = d.x * y0 + d.y * y1 + d.z * y2 + d.w * y3;
+      }
+    }
+    return;
+  }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   if (idx < i1) {
-    i = order[idx];
-    const int64_t p0 = pair0[i];
-    const int n = ns[i];
+    const int4 rec = orec[idx];
+    i = rec.x;
+    const int n = rec.y;
+    const int64_t p0 = (int64_t)(uint32_t)rec.z | ((int64_t)rec.w << 32);
     for (int s = lane; s < n; s += 16) {
       const int ck = nbc[p0 + s];
+      const uint64_t pw = pairs[p0 + s];
       if (LOWER ? ck >= cc : (ck <= cc || ck >= 254)) continue;
-      const int64_t B = (int64_t)(pairs[p0 + s] & 0xffffffffu);
+      const int64_t B = (int64_t)(pw & 0xffffffffu);
       const double* M = lu + 16 * (p0 + s);
-      if (WIDE) {   // one 256-bit load per block row and for the four z entries of the neighbour (other colours: not written by this launch)
-        const double4 zz = ld256(z + B);
+      const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const double4 m = ld256_stream(M + 4 * r);
-          acc[r] += m.x * zz.x + m.y * zz.y + m.z * zz.z + m.w * zz.w;
-        }
-      } else {
-        const double z0 = z[B], z1 = z[B + 1], z2 = z[B + 2], z3 = z[B + 3];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] += M[4 * r] * z0 + M[4 * r + 1] * z1 + M[4 * r + 2] * z2 + M[4 * r + 3] * z3;
-      }
+      for (int r = 0; r < 4; ++r) acc[r] += M[4 * r] * z0 + M[4 * r + 1] * z1 + M[4 * r + 2] * z2 + M[4 * r + 3] * z3;
     }
   }
 #pragma unroll
@@ -311,7 +352,7 @@ k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int32_t* __restrict__ order, c
 void ilu_free(nsgpu_ctx* ctx) {
   IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
   if (!P) return;
-  cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv); cudaFree(P->d_nbc);
+  cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv); cudaFree(P->d_nbc); cudaFree(P->d_orec);
   delete P;
   ctx->ilu = nullptr;
 }
@@ -384,11 +425,13 @@ static int ilu_plan(nsgpu_ctx* ctx, const P1BlockView& V) {
   }
   P->n_colours = (int)P->cstart.size() - 1;
   if (P->cstart.back() != nv) { P->unsupported = true; cleanup(); return NSGPU_OK; }
-  if ((rc = dev_alloc(ctx, &P->d_lu, 16 * ctx->n_pairs)) || (rc = dev_alloc(ctx, &P->d_dinv, 16 * nv)) || (rc = dev_alloc(ctx, &P->d_nbc, ctx->n_pairs))) {
+  if ((rc = dev_alloc(ctx, &P->d_lu, 16 * ctx->n_pairs)) || (rc = dev_alloc(ctx, &P->d_dinv, 16 * nv)) || (rc = dev_alloc(ctx, &P->d_nbc, ctx->n_pairs)) ||
+      (rc = dev_alloc(ctx, &P->d_orec, nv))) {
     cleanup(); ilu_free(ctx); return rc;
   }
   k_ilu_nbc<<<g256(nv * 16), 256, 0, s>>>(nv, ctx->n_owned, V.pair0, V.ns, ctx->d_pairs, P->d_colour, P->d_nbc);
-  ctx->launches += 1;
+  k_ilu_orec<<<g256(nv), 256, 0, s>>>(nv, P->d_order, V.pair0, V.ns, P->d_orec);
+  ctx->launches += 2;
   IL_CUDA(cudaGetLastError());
   cleanup();
 #undef IL_CUDA
@@ -437,13 +480,13 @@ int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z) {
   const bool wide = (reinterpret_cast<uintptr_t>(d_z) & 31) == 0 && (reinterpret_cast<uintptr_t>(P->d_lu) & 31) == 0;   // 256-bit loads
   for (int c = 1; c < P->n_colours; ++c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    if (wide) k_ilu_sweep<true, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
-    else k_ilu_sweep<true, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    if (wide) k_ilu_sweep<true, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_orec, P->d_nbc, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    else k_ilu_sweep<true, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_orec, P->d_nbc, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   for (int c = P->n_colours - 1; c >= 0; --c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    if (wide) k_ilu_sweep<false, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
-    else k_ilu_sweep<false, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_order, P->d_nbc, V.pair0, V.ns, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    if (wide) k_ilu_sweep<false, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_orec, P->d_nbc, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
+    else k_ilu_sweep<false, false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_orec, P->d_nbc, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
   }
   ctx->launches += 2 * P->n_colours - 1;
   NS_CUDA(ctx, cudaGetLastError());
