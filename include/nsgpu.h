@@ -169,7 +169,11 @@ int nsgpu_host_free_pinned(void* p);
 /* Options: "kernel" (NSGPU_KERNEL_*); for the factorised P1-P1 kernels "ws" (1, default: warp-specialised kernel -- two
  * compute warpgroups and a gather warpgroup per SM, tables by cp.async.bulk) and "pipe" (1: software-pipelined 2-CTA kernel
  * when "ws" is off or does not apply; both 0: plain tile kernel); "rowown" (atomics-free row-owner kernel for the spaces /
- * forms without a factorised kernel: 0 never, 1 default: P2-P1 spaces, 2 every such space); "fuse_fj", "stream_host", "stream_chunks", "spmv_blocks";
+ * forms without a factorised kernel: 0 never, 1 default: P2-P1 spaces, 2 every such space) and "rowown_lean" (1, default: the
+ * G-metric form on tetrahedra through row-side records + a short mixed part; 0: unsplit entity blocks); "fuse_fj", "stream_host",
+ * "stream_chunks", "spmv_blocks", "spmv_wide" (1, default: 256-bit loads in the vertex-blocked MatMult when rows and vectors are
+ * 32-byte aligned); "overlap" (0, default: ghost-row / ghost-residual exchanges after the assembly kernel; 1: ghost tiles first,
+ * exchanges on a second stream beside the interior tiles) and "sm_reserve" (SMs left to the exchange kernels when "overlap" is on);
  * "check_finite" (1, default: NaN / Inf scan of every assembled residual, status NSGPU_ENONFINITE);
  * "renumber" (0 never, 1 default: internal vertex-blocked numbering when the caller's W.dofmap.list is not vertex-blocked,
  * 2 always) and "renumber_order" (1 leader-dof order, 2 default: Morton order of the vertices) -- both before nsgpu_set_space. */
