@@ -118,6 +118,7 @@ struct nsgpu_ctx {
   int64_t fused_hits = 0;
   int check_finite = 1;    // scan the owned residual entries for NaN / Inf after every residual assembly (status NSGPU_ENONFINITE)
   int* d_nonfinite = nullptr;
+  bool ilu_packed = true;  // multicolour ILU: keep a second copy of the factor in elimination order (streaming sweeps) when the memory is there
   bool spmv_wide = true;   // vertex-blocked SpMV: 256-bit loads + 4-byte block columns when rows and vectors are 32-byte aligned
   int spmv_blocks = 5;     // vertex-blocked SpMV: resident 256-thread CTAs per SM the kernel is compiled for (4, 5 or 6)
   int stream_chunks = 16;  // tile chunks of the streamed host path
@@ -242,6 +243,9 @@ __device__ __forceinline__ double4 ld256_nc(const double* p) {
   double4 r;
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
+}
+__device__ __forceinline__ void st256(double* p, const double4& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
 __device__ __forceinline__ double4 ld256(const double* p) {
   double4 r;

@@ -29,6 +29,13 @@ struct IluPlan {
   int32_t* d_colour = nullptr;     // per owned vertex
   int32_t* d_order = nullptr;      // vertices sorted by (colour, vertex)
   int4* d_orec = nullptr;          // per position of the order: (vertex, neighbours, first pair lo, hi): one load instead of order -> pair0 / ns
+  // packed factor (streaming sweeps): the off-diagonal blocks in elimination order -- per position of the order the L blocks (lower
+  // colour) then the U blocks (higher colour) of its vertex, the column vertex inline -- refilled from d_lu after every factorisation
+  int4* d_erec = nullptr;          // per position: (vertex, nL | nU << 16, first packed block lo, hi)
+  uint32_t* d_emap = nullptr;      // packed block -> pair index (its source in d_lu)
+  uint32_t* d_ecol = nullptr;      // packed block -> first dof of the column vertex
+  double* d_lue = nullptr;         // 16 doubles per packed block
+  int64_t n_packed = 0;
   std::vector<int64_t> cstart;     // n_colours + 1 offsets into d_order
   double* d_lu = nullptr;          // 16 doubles per (vertex, neighbour) pair, row-major 4x4, indexed like ctx->d_pairs
   double* d_dinv = nullptr;        // 16 doubles per vertex: U_ii^-1
@@ -349,10 +356,93 @@ k_ilu_sweep(int64_t i0, int64_t i1, int cc, const int4* __restrict__ orec, const
   }
 }
 
+// ---- packed factor: counts, fill, refill, sweeps
+__global__ void k_ilu_ecount(int64_t nv, const int4* __restrict__ orec, const uint8_t* __restrict__ nbc, const int32_t* __restrict__ colour,
+                             int64_t* __restrict__ cnt) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx > nv) return;
+  if (idx == nv) { cnt[idx] = 0; return; }
+  const int4 rec = orec[idx];
+  const int64_t p0 = (int64_t)(uint32_t)rec.z | ((int64_t)rec.w << 32);
+  int m = 0;
+  for (int s = 0; s < rec.y; ++s) m += nbc[p0 + s] < 254 ? 1 : 0;      // 254: the vertex itself, 255: another rank's vertex
+  cnt[idx] = m;
+}
+__global__ void k_ilu_efill(int64_t nv, const int4* __restrict__ orec, const uint8_t* __restrict__ nbc, const int32_t* __restrict__ colour,
+                            const uint64_t* __restrict__ pairs, const int64_t* __restrict__ eoff, int4* __restrict__ erec, uint32_t* __restrict__ emap,
+                            uint32_t* __restrict__ ecol) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  const int4 rec = orec[idx];
+  const int64_t p0 = (int64_t)(uint32_t)rec.z | ((int64_t)rec.w << 32);
+  const int cc = colour[rec.x];
+  const int64_t q0 = eoff[idx];
+  int64_t q = q0;
+  int nL = 0, nU = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int s = 0; s < rec.y; ++s) {
+      const int ck = nbc[p0 + s];
+      if (ck >= 254 || (pass == 0 ? ck >= cc : ck <= cc)) continue;
+      emap[q] = (uint32_t)(p0 + s);
+      ecol[q] = (uint32_t)(pairs[p0 + s] & 0xffffffffu);
+      ++q;
+      if (pass == 0) ++nL; else ++nU;
+    }
+  erec[idx] = make_int4(rec.x, nL | (nU << 16), (int)(q0 & 0xffffffffLL), (int)(q0 >> 32));
+}
+// packed blocks <- factor (four lanes per block, one 32-byte row each)
+__global__ void k_ilu_pack(int64_t n_packed, const uint32_t* __restrict__ emap, const double* __restrict__ lu, double* __restrict__ lue) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t >> 2;
+  const int r = (int)(t & 3);
+  if (e >= n_packed) return;
+  st256(lue + 16 * e + 4 * r, ld256_stream(lu + 16 * (int64_t)emap[e] + 4 * r));
+}
+// one colour of the substitution on the packed factor: the blocks of the launch are one contiguous stream
+template <bool LOWER>
+__global__ void __launch_bounds__(256)
+k_ilu_sweep_packed(int64_t i0, int64_t i1, const int4* __restrict__ erec, const uint32_t* __restrict__ ecol, const double* __restrict__ lue,
+                   const double* __restrict__ dinv, double* z) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t idx = i0 + (t >> 4);
+  const int lane = (int)(t & 15), r = lane & 3, slot = lane >> 2;
+  int64_t i = 0;
+  double acc = 0.0;
+  if (idx < i1) {
+    const int4 rec = erec[idx];
+    i = rec.x;
+    const int nL = rec.y & 0xffff, nU = (unsigned)rec.y >> 16;
+    const int64_t q0 = ((int64_t)(uint32_t)rec.z | ((int64_t)rec.w << 32)) + (LOWER ? 0 : nL);
+    const int cnt = LOWER ? nL : nU;
+#pragma unroll 2
+    for (int k = slot; k < cnt; k += 4) {
+      const uint32_t B = ecol[q0 + k];
+      const double4 m = ld256_stream(lue + 16 * (q0 + k) + 4 * r);
+      const double4 zz = ld256(z + B);
+      acc += m.x * zz.x + m.y * zz.y + m.z * zz.z + m.w * zz.w;
+    }
+  }
+  acc += __shfl_down_sync(0xffffffffu, acc, 8, 16);
+  acc += __shfl_down_sync(0xffffffffu, acc, 4, 16);
+  double y = 0.0;
+  if (idx < i1 && slot == 0) y = z[4 * i + r] - acc;
+  if (LOWER) {
+    if (idx < i1 && slot == 0) z[4 * i + r] = y;
+  } else {
+    const double y0 = __shfl_sync(0xffffffffu, y, 0, 16), y1 = __shfl_sync(0xffffffffu, y, 1, 16);
+    const double y2 = __shfl_sync(0xffffffffu, y, 2, 16), y3 = __shfl_sync(0xffffffffu, y, 3, 16);
+    if (idx < i1 && slot == 0) {
+      const double4 d = ld256_nc(dinv + 16 * i + 4 * r);
+      z[4 * i + r] = d.x * y0 + d.y * y1 + d.z * y2 + d.w * y3;
+    }
+  }
+}
+
 void ilu_free(nsgpu_ctx* ctx) {
   IluPlan* P = static_cast<IluPlan*>(ctx->ilu);
   if (!P) return;
   cudaFree(P->d_colour); cudaFree(P->d_order); cudaFree(P->d_lu); cudaFree(P->d_dinv); cudaFree(P->d_nbc); cudaFree(P->d_orec);
+  cudaFree(P->d_erec); cudaFree(P->d_emap); cudaFree(P->d_ecol); cudaFree(P->d_lue);
   delete P;
   ctx->ilu = nullptr;
 }
@@ -433,6 +523,36 @@ static int ilu_plan(nsgpu_ctx* ctx, const P1BlockView& V) {
   k_ilu_orec<<<g256(nv), 256, 0, s>>>(nv, P->d_order, V.pair0, V.ns, P->d_orec);
   ctx->launches += 2;
   IL_CUDA(cudaGetLastError());
+  // packed factor tables (optional: without the memory for a second copy of the blocks the sweeps walk d_lu through the neighbour lists)
+  if (ctx->ilu_packed) {
+    int64_t *d_ecnt = nullptr, *d_eoff = nullptr;
+    void* d_tmp2 = nullptr;
+    bool ok = cudaMalloc(&d_ecnt, sizeof(int64_t) * (nv + 1)) == cudaSuccess && cudaMalloc(&d_eoff, sizeof(int64_t) * (nv + 1)) == cudaSuccess;
+    if (ok) {
+      k_ilu_ecount<<<g256(nv + 1), 256, 0, s>>>(nv, P->d_orec, P->d_nbc, P->d_colour, d_ecnt);
+      size_t tb = 0;
+      ok = cub::DeviceScan::ExclusiveSum(nullptr, tb, d_ecnt, d_eoff, nv + 1, s) == cudaSuccess && cudaMalloc(&d_tmp2, tb) == cudaSuccess &&
+           cub::DeviceScan::ExclusiveSum(d_tmp2, tb, d_ecnt, d_eoff, nv + 1, s) == cudaSuccess;
+    }
+    int64_t np = 0;
+    if (ok) ok = cudaMemcpyAsync(&np, d_eoff + nv, sizeof(int64_t), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+    if (ok && np > 0 && np < (int64_t(1) << 32) && ctx->n_pairs < (int64_t(1) << 32)) {
+      ok = cudaMalloc(&P->d_erec, sizeof(int4) * nv) == cudaSuccess && cudaMalloc(&P->d_emap, sizeof(uint32_t) * np) == cudaSuccess &&
+           cudaMalloc(&P->d_ecol, sizeof(uint32_t) * np) == cudaSuccess && cudaMalloc(&P->d_lue, sizeof(double) * 16 * np) == cudaSuccess;
+      if (ok) {
+        k_ilu_efill<<<g256(nv), 256, 0, s>>>(nv, P->d_orec, P->d_nbc, P->d_colour, ctx->d_pairs, d_eoff, P->d_erec, P->d_emap, P->d_ecol);
+        ok = cudaStreamSynchronize(s) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        ctx->launches += 2;
+        P->n_packed = np;
+      }
+    } else ok = false;
+    if (!ok) {   // not fatal: fall back to the unpacked sweeps
+      cudaGetLastError();
+      cudaFree(P->d_erec); cudaFree(P->d_emap); cudaFree(P->d_ecol); cudaFree(P->d_lue);
+      P->d_erec = nullptr; P->d_emap = nullptr; P->d_ecol = nullptr; P->d_lue = nullptr; P->n_packed = 0;
+    }
+    cudaFree(d_ecnt); cudaFree(d_eoff); cudaFree(d_tmp2);
+  }
   cleanup();
 #undef IL_CUDA
   return NSGPU_OK;
@@ -460,6 +580,10 @@ int ilu_factor(nsgpu_ctx* ctx) {
                                                                    P->d_dinv, d_sing);
   }
   ctx->launches += 1 + P->n_colours;
+  if (P->d_lue) {
+    k_ilu_pack<<<g256(P->n_packed * 4), 256, 0, s>>>(P->n_packed, P->d_emap, P->d_lu, P->d_lue);
+    ctx->launches += 1;
+  }
   int sing = 0;
   cudaError_t e = cudaMemcpyAsync(&sing, d_sing, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -478,6 +602,19 @@ int ilu_apply(nsgpu_ctx* ctx, const double* d_r, double* d_z) {
   cudaStream_t s = ctx->stream;
   if (d_z != d_r) NS_CUDA(ctx, cudaMemcpyAsync(d_z, d_r, sizeof(double) * (size_t)ctx->n_owned, cudaMemcpyDeviceToDevice, s));
   const bool wide = (reinterpret_cast<uintptr_t>(d_z) & 31) == 0 && (reinterpret_cast<uintptr_t>(P->d_lu) & 31) == 0;   // 256-bit loads
+  if (wide && P->d_lue) {
+    for (int c = 1; c < P->n_colours; ++c) {
+      const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
+      k_ilu_sweep_packed<true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, P->d_erec, P->d_ecol, P->d_lue, P->d_dinv, d_z);
+    }
+    for (int c = P->n_colours - 1; c >= 0; --c) {
+      const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
+      k_ilu_sweep_packed<false><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, P->d_erec, P->d_ecol, P->d_lue, P->d_dinv, d_z);
+    }
+    ctx->launches += 2 * P->n_colours - 1;
+    NS_CUDA(ctx, cudaGetLastError());
+    return NSGPU_OK;
+  }
   for (int c = 1; c < P->n_colours; ++c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
     if (wide) k_ilu_sweep<true, true><<<g256((i1 - i0) * 16), 256, 0, s>>>(i0, i1, c, P->d_orec, P->d_nbc, ctx->d_pairs, P->d_lu, P->d_dinv, d_z);
