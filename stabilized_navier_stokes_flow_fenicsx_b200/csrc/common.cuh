@@ -118,6 +118,7 @@ struct nsgpu_ctx {
   int64_t fused_hits = 0;
   int check_finite = 1;    // scan the owned residual entries for NaN / Inf after every residual assembly (status NSGPU_ENONFINITE)
   int* d_nonfinite = nullptr;
+  bool ilu_factor16 = true; // multicolour ILU: sixteen lanes per vertex in the factorisation when no block row is longer than 16
   bool ilu_packed = true;  // multicolour ILU: keep a second copy of the factor in elimination order (streaming sweeps) when the memory is there
   bool spmv_wide = true;   // vertex-blocked SpMV: 256-bit loads + 4-byte block columns when rows and vectors are 32-byte aligned
   int spmv_blocks = 5;     // vertex-blocked SpMV: resident 256-thread CTAs per SM the kernel is compiled for (4, 5 or 6)

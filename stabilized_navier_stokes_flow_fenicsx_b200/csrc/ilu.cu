@@ -36,6 +36,7 @@ struct IluPlan {
   uint32_t* d_ecol = nullptr;      // packed block -> first dof of the column vertex
   double* d_lue = nullptr;         // 16 doubles per packed block
   int64_t n_packed = 0;
+  int max_ns = 0;                  // longest block row (the 16-lane factorisation kernel takes rows of at most 16 blocks)
   std::vector<int64_t> cstart;     // n_colours + 1 offsets into d_order
   double* d_lu = nullptr;          // 16 doubles per (vertex, neighbour) pair, row-major 4x4, indexed like ctx->d_pairs
   double* d_dinv = nullptr;        // 16 doubles per vertex: U_ii^-1
@@ -268,6 +269,110 @@ k_ilu_factor(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __r
   }
   if (!blk_inverse(D, Di)) *singular = 1;
   blk_store(dinv + 16 * i, Di);
+}
+
+// The same factorisation with sixteen lanes per vertex (rows of at most 16 blocks): lane t keeps block (i, slot t) in registers from the
+// first elimination step to the last; per step the lanes agree on the next earlier neighbour k (minimum of the (colour, vertex) keys
+// above the last one), the lane that holds A_ik turns it into L_ik = A_ik U_kk^-1 and hands it round through shared memory, and every
+// lane whose column comes after k looks (k, j) up in row k and updates its block.  Same operations per block in the same order as
+// k_ilu_factor (bitwise the same factor); the dependent loads per vertex drop from (earlier neighbours x slots x search steps) to
+// (earlier neighbours x search steps).
+__global__ void __launch_bounds__(128)
+k_ilu_factor16(int64_t i0, int64_t i1, int cc, int64_t n_owned, const int32_t* __restrict__ order, const int32_t* __restrict__ colour,
+               const int64_t* __restrict__ pair0, const int32_t* __restrict__ ns, const uint64_t* __restrict__ pairs, double* lu, double* dinv,
+               int* singular) {
+  __shared__ double sL[8][16];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const unsigned gm = 0xffffu << (16 * (grp & 1));
+  const int64_t idx = i0 + (int64_t)blockIdx.x * 8 + grp;
+  const bool valid = idx < i1;
+  const int64_t i = valid ? order[idx] : 0;
+  const int64_t p0 = valid ? pair0[i] : 0;
+  const int n = valid ? ns[i] : 0;
+  const long long NONE = 0x7fffffffffffffffLL;
+  int64_t B = -1, kv = -1;
+  int ck = 255;
+  double A[4][4];
+  bool owned = false;
+  if (lane < n) {
+    B = (int64_t)(pairs[p0 + lane] & 0xffffffffu);
+    owned = B < n_owned;
+    if (owned) {
+      kv = B >> 2;
+      ck = kv == i ? cc : colour[kv];
+      blk_load(lu + 16 * (p0 + lane), A);
+    }
+  }
+  const bool isdiag = owned && kv == i;
+  const long long key = (owned && !isdiag && ck < cc) ? (((long long)ck << 32) | kv) : NONE;
+  long long last = -1;
+  for (;;) {
+    long long best = key > last ? key : NONE;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const long long other = __shfl_xor_sync(gm, best, o, 16);
+      best = other < best ? other : best;
+    }
+    if (best == NONE) break;                                  // uniform over the group
+    last = best;
+    const int64_t k = best & 0xffffffffLL;
+    const int ckk = (int)(best >> 32);
+    if (key == best) {                                        // L_ik = A_ik U_kk^-1
+      double Dk[4][4], L[4][4];
+      blk_load(dinv + 16 * k, Dk);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) L[r][c] = A[r][0] * Dk[0][c] + A[r][1] * Dk[1][c] + A[r][2] * Dk[2][c] + A[r][3] * Dk[3][c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { A[r][c] = L[r][c]; sL[grp][4 * r + c] = L[r][c]; }
+    }
+    __syncwarp(gm);
+    if (owned && key != best) {
+      const int cj = isdiag ? cc : ck;
+      if (!(cj < ckk || (cj == ckk && kv < k))) {             // j after k: (k, j) in row k?  neighbour lists are sorted by first dof
+        const int64_t q0 = pair0[k];
+        int lo = 0, hi = ns[k] - 1, u = -1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const int64_t Bm = (int64_t)(pairs[q0 + mid] & 0xffffffffu);
+          if (Bm == B) { u = mid; break; }
+          if (Bm < B) lo = mid + 1; else hi = mid - 1;
+        }
+        if (u >= 0) {
+          double U[4][4];
+          blk_load(lu + 16 * (q0 + u), U);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              A[r][c] -= sL[grp][4 * r] * U[0][c] + sL[grp][4 * r + 1] * U[1][c] + sL[grp][4 * r + 2] * U[2][c] + sL[grp][4 * r + 3] * U[3][c];
+        }
+      }
+    }
+    __syncwarp(gm);
+  }
+  if (owned) blk_store(lu + 16 * (p0 + lane), A);
+  const unsigned anyd = __ballot_sync(gm, isdiag) & gm;
+  if (isdiag) {
+    double Di[4][4];
+    if (!blk_inverse(A, Di)) *singular = 1;
+    blk_store(dinv + 16 * i, Di);
+  } else if (valid && anyd == 0 && lane == 0) {               // no diagonal block in the pattern: identity, as in k_ilu_factor
+    double Di[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Di[r][c] = (r == c) ? 1.0 : 0.0;
+    blk_store(dinv + 16 * i, Di);
+  }
+}
+
+__global__ void k_ilu_maxns(int64_t nv, const int32_t* __restrict__ ns, int* out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < nv) atomicMax(out, ns[e]);
 }
 
 // one colour of the forward (LOWER: z_i -= sum over earlier neighbours L_ik z_k) or backward (z_i = U_ii^-1 (z_i - sum over later
@@ -523,6 +628,11 @@ static int ilu_plan(nsgpu_ctx* ctx, const P1BlockView& V) {
   k_ilu_orec<<<g256(nv), 256, 0, s>>>(nv, P->d_order, V.pair0, V.ns, P->d_orec);
   ctx->launches += 2;
   IL_CUDA(cudaGetLastError());
+  IL_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+  k_ilu_maxns<<<g256(nv), 256, 0, s>>>(nv, V.ns, d_flag);
+  IL_CUDA(cudaMemcpyAsync(&P->max_ns, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  IL_CUDA(cudaStreamSynchronize(s));
+  ctx->launches += 1;
   // packed factor tables (optional: without the memory for a second copy of the blocks the sweeps walk d_lu through the neighbour lists)
   if (ctx->ilu_packed) {
     int64_t *d_ecnt = nullptr, *d_eoff = nullptr;
@@ -576,8 +686,12 @@ int ilu_factor(nsgpu_ctx* ctx) {
   k_ilu_load<<<g256(P->nv * 16), 256, 0, s>>>(P->nv, ctx->n_owned, V.pair0, V.ns, ctx->d_pairs, V.rowpos, ctx->d_vals, P->d_lu);
   for (int c = 0; c < P->n_colours; ++c) {
     const int64_t i0 = P->cstart[c], i1 = P->cstart[c + 1];
-    k_ilu_factor<<<(unsigned)ceil_div(i1 - i0, 64), 64, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu,
-                                                                   P->d_dinv, d_sing);
+    if (P->max_ns <= 16 && ctx->ilu_factor16)
+      k_ilu_factor16<<<(unsigned)ceil_div(i1 - i0, 8), 128, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu,
+                                                                      P->d_dinv, d_sing);
+    else
+      k_ilu_factor<<<(unsigned)ceil_div(i1 - i0, 64), 64, 0, s>>>(i0, i1, c, ctx->n_owned, P->d_order, P->d_colour, V.pair0, V.ns, ctx->d_pairs, P->d_lu,
+                                                                     P->d_dinv, d_sing);
   }
   ctx->launches += 1 + P->n_colours;
   if (P->d_lue) {

@@ -42,6 +42,10 @@ def test_ilu_application_matches_the_block_ilu0_restatement():
     assert e_ilu < 0.9
     z2 = asm.ilu_apply(r)                       # same colouring, same factors: bitwise reproducible
     assert np.array_equal(z, z2)
+    asm.set_option("ilu_factor16", 0)           # one thread per vertex instead of sixteen lanes: the same operations per block
+    z4 = asm.ilu_apply(r)
+    assert np.abs(z4 - z).max() <= 1e-13 * np.abs(z).max()
+    asm.set_option("ilu_factor16", 1)
     asm.set_option("ilu_packed", 0)             # sweeps through the neighbour lists instead of the packed copy of the factor
     z3 = asm.ilu_apply(r)
     assert np.abs(z3 - zr).max() <= 1e-10 * np.abs(zr).max() and np.abs(z3 - z).max() <= 1e-12 * np.abs(z).max()
