@@ -1,14 +1,14 @@
 // p1tet_ws.cuh -- warp-specialised row-owner kernel (included by p1tet.cu after the tile kernels).
 //
-// One persistent CTA per SM, 384 threads = three warpgroups, one warp of each per SM sub-partition:
-//   * two COMPUTE warpgroups (216 registers/thread after setmaxnreg) evaluate the row slabs of alternate tiles
+// One persistent CTA per SM, 512 threads = four warpgroups, one warp of each per SM sub-partition:
+//   * two COMPUTE warpgroups (208 registers/thread after setmaxnreg.inc) evaluate the row slabs of alternate tiles
 //     (phase A of p1tet.cu: element algebra of NavierStokes/NavierStokesChannelFlow.py:220-251, one incidence per thread)
 //     and park them in a ring of three staging buffers;
-//   * one GATHER warpgroup (72 registers/thread) sums the parked blocks into finished 32-byte pieces of the CSR rows and
-//     the residual entries, and streams them out (phase B).
+//   * two GATHER warpgroups (48 registers/thread after setmaxnreg.dec) sum the parked blocks of alternate tiles into finished
+//     32-byte pieces of the CSR rows and the residual entries, and stream them out (phase B).
 // A sub-partition's fp64 pipe therefore always has two algebra warps to choose from, and the gather / store / table
 // latencies run beside the algebra instead of between two algebra phases of the same warps (the 2-CTA pipelined kernel
-// keeps the pipe 38 % busy: profiles/r1c_ncu_full_L_p1tet_pipe.txt).
+// keeps the pipe 38 % busy: profiles/r1c_ncu_full_L_p1tet_pipe.txt; this one 44 %: profiles/r2_ncu_full_L_p1tet_ws.txt).
 //
 // Data movement: every per-tile table is ONE contiguous blob in HBM, fetched by one elected thread with
 // cp.async.bulk (TMA engine, completion on an mbarrier) two to three tiles ahead:
